@@ -1,0 +1,109 @@
+// emu_team.cu — CPU emulation of ONE team (64 threads) of the blind-rotation kernel.
+//
+// TEST INFRASTRUCTURE: this container has no GPU, so the `-m "not gpu"` tests run the very same
+// __host__ __device__ team code (negacyclic_fft.cuh, blind_rotate.cuh) with 64 CPU threads and pthread
+// barriers, and compare it with the oracle.  Never loaded by the product path.
+#include <pthread.h>
+#include <stdlib.h>
+#include <vector>
+#include "blind_rotate.cuh"
+#include "twiddles_host.h"
+
+using namespace peba1;
+
+namespace {
+
+struct HostEnv {
+    int tid;
+    pthread_barrier_t* team;
+    pthread_barrier_t* warp;
+    void team_sync() { pthread_barrier_wait(team); }
+    void warp_sync() { pthread_barrier_wait(warp); }
+    int32_t ldg(const int32_t* p) const { return *p; }
+    double2 ldg2(const double2* p) const { return *p; }
+};
+
+struct Shared {
+    TeamSmem sm;
+    TwiddleTables tables;
+    pthread_barrier_t team, warp[2];
+    // work description
+    int mode;  // 0 key transform, 1 bootstrap
+    int L, Bgbit, n, rows;
+    const int32_t* bk;
+    double2* bkfft;
+    const int32_t* in_ct;
+    int32_t* u_out;
+    int64_t count;
+};
+
+struct ThreadArg { Shared* S; int tid; };
+
+void* worker(void* p) {
+    ThreadArg* A = (ThreadArg*)p;
+    Shared* S = A->S;
+    HostEnv env{A->tid, &S->team, &S->warp[A->tid >> 5]};
+    TeamTwiddles tw;
+    load_team_twiddles(S->tables, A->tid, tw);
+    if (S->mode == 0) {
+        const int polys = S->n * S->rows * 2;
+        for (int q = 0; q < polys; ++q) {
+            const int c = q & 1, ir = q >> 1;
+            key_transform_team(env, S->sm, tw, S->bk + (size_t)q * kN,
+                               S->bkfft + bkfft_index(S->rows, ir / S->rows, ir % S->rows, 0, c, 0));
+        }
+    } else {
+        for (int64_t g = 0; g < S->count; ++g) {
+            PbsJob job{0, -1, 0, 1, 0};
+            const int32_t* pool = S->in_ct + (size_t)g * (S->n + 1);
+            int32_t* u = S->u_out + (size_t)g * (kN + 1);
+            if (S->L == 3 && S->Bgbit == 7)
+                blind_rotate_team<3, 7>(env, S->sm, tw, S->bkfft, S->n, pool, S->n + 1, job, u);
+            else
+                blind_rotate_team<2, 10>(env, S->sm, tw, S->bkfft, S->n, pool, S->n + 1, job, u);
+        }
+    }
+    return nullptr;
+}
+
+int run(Shared* S) {
+    build_twiddle_tables(S->tables);
+    pthread_barrier_init(&S->team, nullptr, kTeam);
+    pthread_barrier_init(&S->warp[0], nullptr, 32);
+    pthread_barrier_init(&S->warp[1], nullptr, 32);
+    std::vector<pthread_t> th(kTeam);
+    std::vector<ThreadArg> args(kTeam);
+    for (int t = 0; t < kTeam; ++t) { args[t] = {S, t}; pthread_create(&th[t], nullptr, worker, &args[t]); }
+    for (int t = 0; t < kTeam; ++t) pthread_join(th[t], nullptr);
+    pthread_barrier_destroy(&S->team);
+    pthread_barrier_destroy(&S->warp[0]);
+    pthread_barrier_destroy(&S->warp[1]);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// bk: int32 [n][rows][2][1024] -> bkfft: double2 [n][rows][8][2][64]
+int peba1_emu_key_transform(const int32_t* bk, int n, int rows, double* bkfft_out) {
+    Shared* S = new Shared();
+    S->mode = 0; S->n = n; S->rows = rows; S->bk = bk; S->bkfft = (double2*)bkfft_out;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+// in: count samples of n+1 words; out: count extracted samples of 1025 words
+int peba1_emu_bootstrap_woks(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                             int64_t count) {
+    if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
+    Shared* S = new Shared();
+    S->mode = 1; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
+    S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,870 @@
+// peba1_cuda.cu — libpeba1_cuda: the sm_100a gate-bootstrapping engine behind include/peba1_cuda.h.
+//
+// Kernels:
+//   K0+K1  pbs_kernel          gate prologue, mod-switch, 630-step blind rotation, sample extraction
+//                              (replaces tfhe_bootstrap_woKS_FFT and everything below it)
+//   K2     keyswitch_kernel    lweKeySwitch over the extracted samples, writes the ciphertext pool
+//   K3     key_transform_kernel bootstrapping key -> transform domain, once per key
+//   K4     linear_kernel       bootsNOT / bootsCOPY / bootsCONSTANT on pool slots
+// There is no CPU fallback in this file: every entry point needs a CUDA device.
+#include "../../include/peba1_cuda.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "blind_rotate.cuh"
+#include "twiddles_host.h"
+
+using namespace peba1;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(PEBA1_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                        \
+    } while (0)
+
+extern "C" const char* peba1_cuda_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------ device side
+namespace {
+
+constexpr int kPoolPad = 4;        // pool stride is (n+1) rounded up to a multiple of 4 words (16-byte rows)
+constexpr int kUStride = kN + 4;   // extracted sample: 1025 words, padded to 1028
+
+struct DevEnv {
+    int tid;      // thread index inside the team
+    int bar_id;   // named barrier owned by the team (1..15)
+    __device__ __forceinline__ void team_sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTeam) : "memory"); }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    __device__ __forceinline__ int32_t ldg(const int32_t* p) const { return __ldg(p); }
+    __device__ __forceinline__ double2 ldg2(const double2* p) const { return __ldg(p); }
+};
+
+__constant__ TwiddleTables c_tables;
+
+__device__ __forceinline__ void load_twiddles_dev(int tid, TeamTwiddles& tw) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        tw.tw1[j] = c_tables.tw1[tid][j];
+        tw.tw2[j] = c_tables.tw2[tid & 7][j];
+    }
+}
+
+// One keyswitch job: out_slot <- KS( (0,c0) + u[u0] + u[u1] ), u1 < 0: absent (non-MUX gates).
+struct __align__(16) KsJob {
+    int32_t u0, u1;
+    int32_t c0;
+    int32_t pad;
+    int64_t out_slot;
+};
+
+// K0+K1.  One team of 64 threads per bootstrap, TEAMS teams per CTA; job index = blockIdx.x*TEAMS + team.
+template <int L, int BGBIT, int TEAMS>
+__global__ void __launch_bounds__(TEAMS* kTeam, 1)
+    pbs_kernel(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
+               const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TeamSmem* teams = reinterpret_cast<TeamSmem*>(smem_raw);
+    const int team = threadIdx.x / kTeam;
+    const int64_t g = (int64_t)blockIdx.x * TEAMS + team;
+    if (g >= count) return;  // whole team leaves together; named barriers are per team
+    DevEnv env{(int)(threadIdx.x % kTeam), team + 1};
+    TeamTwiddles tw;
+    load_twiddles_dev(env.tid, tw);
+    blind_rotate_team<L, BGBIT>(env, teams[team], tw, bkfft, n, pool, pool_stride, jobs[g],
+                                u_out + g * (int64_t)kUStride);
+}
+
+// K3.  One team per key polynomial q = (i*rows + r)*2 + c.
+template <int TEAMS>
+__global__ void __launch_bounds__(TEAMS* kTeam, 1)
+    key_transform_kernel(const int32_t* __restrict__ bk, int rows, int64_t polys, double2* __restrict__ bkfft) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TeamSmem* teams = reinterpret_cast<TeamSmem*>(smem_raw);
+    const int team = threadIdx.x / kTeam;
+    const int64_t q = (int64_t)blockIdx.x * TEAMS + team;
+    if (q >= polys) return;
+    DevEnv env{(int)(threadIdx.x % kTeam), team + 1};
+    TeamTwiddles tw;
+    load_twiddles_dev(env.tid, tw);
+    const int c = (int)(q & 1);
+    const int64_t ir = q >> 1;
+    key_transform_team(env, teams[team], tw, bk + q * kN,
+                       bkfft + bkfft_index(rows, (int)(ir / rows), (int)(ir % rows), 0, c, 0));
+}
+
+// K2.  One CTA per keyswitch job.  Thread t owns output words 4t..4t+3 (row stride is a multiple of 4 words).
+// KSK device layout: [i][j][d-1][stride] (the all-zero digit-0 rows are dropped).
+constexpr int kKsThreads = 160;
+
+template <int T, int BASEBIT>
+__global__ void __launch_bounds__(kKsThreads)
+    keyswitch_kernel(const int32_t* __restrict__ ksk, int n, int64_t stride, const int32_t* __restrict__ u,
+                     const KsJob* __restrict__ jobs, int32_t* __restrict__ pool) {
+    constexpr int BASE = 1 << BASEBIT;
+    constexpr uint32_t PREC_OFFSET = 1u << (32 - (1 + BASEBIT * T));
+    __shared__ uint32_t abar[kN];
+    const KsJob job = jobs[blockIdx.x];
+    const int32_t* u0 = u + (int64_t)job.u0 * kUStride;
+    const int32_t* u1 = job.u1 >= 0 ? u + (int64_t)job.u1 * kUStride : nullptr;
+    for (int i = threadIdx.x; i < kN; i += blockDim.x) {
+        uint32_t a = (uint32_t)u0[i];
+        if (u1) a += (uint32_t)u1[i];
+        abar[i] = a + PREC_OFFSET;
+    }
+    __syncthreads();
+    const int w0 = 4 * threadIdx.x;
+    if (w0 > n) return;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const uint4* base = reinterpret_cast<const uint4*>(ksk) + threadIdx.x;
+    const int64_t row4 = stride / 4;
+    for (int i = 0; i < kN; ++i) {
+        const uint32_t a = abar[i];
+        uint4 v[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const uint32_t d = (a >> (32 - (j + 1) * BASEBIT)) & (BASE - 1);
+            v[j] = make_uint4(0, 0, 0, 0);
+            if (d != 0) v[j] = __ldg(base + (((int64_t)i * T + j) * (BASE - 1) + (d - 1)) * row4);
+        }
+#pragma unroll
+        for (int j = 0; j < T; ++j) { acc.x -= v[j].x; acc.y -= v[j].y; acc.z -= v[j].z; acc.w -= v[j].w; }
+    }
+    // b' (+ b'' + c0) goes to word n
+    uint32_t bsum = (uint32_t)u0[kN] + (uint32_t)job.c0;
+    if (u1) bsum += (uint32_t)u1[kN];
+    uint32_t r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (w0 + q == n) r[q] += bsum;
+    int32_t* out = pool + job.out_slot * stride;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (w0 + q <= n) out[w0 + q] = (int32_t)r[q];
+}
+
+// K4.  out = sign*in + (0, cst); in < 0: absent.
+__global__ void linear_kernel(int32_t* __restrict__ pool, int64_t stride, int n, const int64_t* __restrict__ in,
+                              const int32_t* __restrict__ sign, const int32_t* __restrict__ cst,
+                              const int64_t* __restrict__ out) {
+    const int64_t g = blockIdx.x;
+    const int64_t src = in[g];
+    const uint32_t s = (uint32_t)sign[g];
+    for (int w = threadIdx.x; w <= n; w += blockDim.x) {
+        uint32_t v = src >= 0 ? s * (uint32_t)pool[src * stride + w] : 0u;
+        if (w == n) v += (uint32_t)cst[g];
+        pool[out[g] * stride + w] = (int32_t)v;
+    }
+}
+
+// pool initialisation: trivial false (a = 0, b = -1/8) — SURVEY.md §8a quirk Q2.
+__global__ void pool_init_kernel(int32_t* __restrict__ pool, int64_t stride, int n, int64_t first, int64_t slots) {
+    const int64_t total = slots * stride;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(idx % stride);
+        pool[first * stride + idx] = (w == n) ? -(1 << 29) : 0;
+    }
+}
+
+// repack of the keyswitch key: [i][j][d][n+1] -> [i][j][d-1][stride]
+__global__ void ksk_pack_kernel(const int32_t* __restrict__ src, int n, int base, int64_t stride, int64_t rows_out,
+                                int32_t* __restrict__ dst) {
+    const int64_t r = blockIdx.x;  // output row = (i*t + j)*(base-1) + (d-1)
+    if (r >= rows_out) return;
+    const int64_t ij = r / (base - 1);
+    const int d = (int)(r % (base - 1)) + 1;
+    const int32_t* s = src + (ij * base + d) * (int64_t)(n + 1);
+    for (int w = threadIdx.x; w < stride; w += blockDim.x) dst[r * stride + w] = w <= n ? s[w] : 0;
+}
+
+// scatter / gather between a dense staging buffer [count][n+1] and pool slots
+__global__ void scatter_kernel(int32_t* __restrict__ pool, int64_t stride, int n, const int64_t* __restrict__ slots,
+                               int64_t first_slot, const int32_t* __restrict__ dense) {
+    const int64_t g = blockIdx.x;
+    const int64_t s = slots ? slots[g] : first_slot + g;
+    for (int w = threadIdx.x; w <= n; w += blockDim.x) pool[s * stride + w] = dense[g * (n + 1) + w];
+}
+__global__ void gather_kernel(const int32_t* __restrict__ pool, int64_t stride, int n,
+                              const int64_t* __restrict__ slots, int64_t first_slot, int32_t* __restrict__ dense) {
+    const int64_t g = blockIdx.x;
+    const int64_t s = slots ? slots[g] : first_slot + g;
+    for (int w = threadIdx.x; w <= n; w += blockDim.x) dense[g * (n + 1) + w] = pool[s * stride + w];
+}
+// u (padded stride) <-> dense [count][N+1]
+__global__ void u_unpad_kernel(int32_t* __restrict__ u, int32_t* __restrict__ dense, int to_dense) {
+    const int64_t g = blockIdx.x;
+    for (int w = threadIdx.x; w <= kN; w += blockDim.x) {
+        if (to_dense) dense[g * (kN + 1) + w] = u[g * kUStride + w];
+        else u[g * kUStride + w] = dense[g * (kN + 1) + w];
+    }
+}
+
+// FP64 FMA peak probe: 8 independent DFMA chains per thread.
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+struct peba1_cuda_ctx {
+    int device = 0;
+    int sm_count = 0;
+    peba1_cuda_params p{};
+    int rows = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // keys
+    double2* bkfft = nullptr;
+    size_t bkfft_bytes = 0;
+    int32_t* ksk = nullptr;
+    size_t ksk_bytes = 0;
+    bool bk_loaded = false, ksk_loaded = false;
+    // pool
+    int32_t* pool = nullptr;
+    int64_t pool_slots = 0, pool_stride = 0;
+    // workspaces (grown on demand)
+    int32_t* u = nullptr;
+    int64_t u_cap = 0;  // in samples
+    void* d_jobs = nullptr;
+    size_t d_jobs_cap = 0;
+    void* h_jobs = nullptr;  // pinned
+    size_t h_jobs_cap = 0;
+    int32_t* d_stage = nullptr;  // dense staging for uploads/downloads
+    size_t d_stage_cap = 0;
+    int32_t* h_stage = nullptr;  // pinned
+    size_t h_stage_cap = 0;
+    // options
+    int teams_per_cta = 4;
+    int64_t max_pbs_per_launch = 1 << 18;
+    // stats
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    peba1_cuda_stats stats{};
+};
+
+namespace {
+
+int ensure_dev(void** ptr, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    size_t want = std::max(need, (size_t)1 << 20);
+    CU(cudaMalloc(ptr, want));
+    *cap = want;
+    return 0;
+}
+int ensure_pinned(void** ptr, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*ptr) cudaFreeHost(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    size_t want = std::max(need, (size_t)1 << 20);
+    CU(cudaMallocHost(ptr, want));
+    *cap = want;
+    return 0;
+}
+
+int use_device(peba1_cuda_ctx* c) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    return 0;
+}
+
+bool params_supported(const peba1_cuda_params& p) {
+    if (p.N != kN || p.k != 1) return false;
+    if (!((p.l == 3 && p.Bgbit == 7) || (p.l == 2 && p.Bgbit == 10))) return false;
+    if (p.ks_t != 8 || p.ks_basebit != 2) return false;
+    if (p.n < 1 || p.n > 639) return false;
+    return true;
+}
+
+size_t team_smem_bytes(int teams) { return sizeof(TeamSmem) * (size_t)teams; }
+
+template <int TEAMS>
+int launch_pbs_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
+                 int32_t* u) {
+    const size_t smem = team_smem_bytes(TEAMS);
+    const unsigned grid = (unsigned)((count + TEAMS - 1) / TEAMS);
+    if (c->p.l == 3) {
+        auto k = pbs_kernel<3, 7, TEAMS>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, TEAMS * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+    } else {
+        auto k = pbs_kernel<2, 10, TEAMS>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, TEAMS * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+    }
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    return 0;
+}
+
+int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
+               int32_t* u) {
+    if (count <= 0) return 0;
+    if (c->timing) CU(cudaEventRecord(c->ev0, c->stream));
+    int rc;
+    switch (c->teams_per_cta) {
+        case 1: rc = launch_pbs_t<1>(c, pool, stride, jobs, count, u); break;
+        case 2: rc = launch_pbs_t<2>(c, pool, stride, jobs, count, u); break;
+        case 3: rc = launch_pbs_t<3>(c, pool, stride, jobs, count, u); break;
+        case 6: rc = launch_pbs_t<6>(c, pool, stride, jobs, count, u); break;
+        default: rc = launch_pbs_t<4>(c, pool, stride, jobs, count, u); break;
+    }
+    if (rc) return rc;
+    if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
+    c->stats.pbs += (uint64_t)count;
+    return 0;
+}
+
+int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t count, int32_t* pool) {
+    if (count <= 0) return 0;
+    keyswitch_kernel<8, 2><<<(unsigned)count, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, pool);
+    CU(cudaGetLastError());
+    if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
+    c->stats.launches++;
+    c->stats.keyswitches += (uint64_t)count;
+    return 0;
+}
+
+int collect_timing(peba1_cuda_ctx* c, bool pbs, bool ks) {
+    if (!c->timing) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    if (pbs) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->stats.last_blind_rotate_ms = ms;
+        c->stats.sum_blind_rotate_ms += ms;
+    }
+    if (ks) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev1, c->ev2));
+        c->stats.last_keyswitch_ms = ms;
+        c->stats.sum_keyswitch_ms += ms;
+    }
+    return 0;
+}
+
+// gate constants: c0 in eighths of the torus, sa, sb
+bool gate_consts(int op, int* c0, int* sa, int* sb) {
+    switch (op) {
+        case PEBA1_OP_NAND: *c0 = 1; *sa = -1; *sb = -1; return true;
+        case PEBA1_OP_AND: *c0 = -1; *sa = 1; *sb = 1; return true;
+        case PEBA1_OP_OR: *c0 = 1; *sa = 1; *sb = 1; return true;
+        case PEBA1_OP_XOR: *c0 = 2; *sa = 2; *sb = 2; return true;
+        case PEBA1_OP_XNOR: *c0 = -2; *sa = -2; *sb = -2; return true;
+        case PEBA1_OP_NOR: *c0 = -1; *sa = -1; *sb = -1; return true;
+        case PEBA1_OP_ANDNY: *c0 = -1; *sa = -1; *sb = 1; return true;
+        case PEBA1_OP_ANDYN: *c0 = -1; *sa = 1; *sb = -1; return true;
+        case PEBA1_OP_ORNY: *c0 = 1; *sa = -1; *sb = 1; return true;
+        case PEBA1_OP_ORYN: *c0 = 1; *sa = 1; *sb = -1; return true;
+        default: return false;
+    }
+}
+constexpr uint32_t kEighth = 1u << 29;
+
+// operand q of gate g with multiplier s: fills (slot, sign) and returns the constant contribution to b.
+inline uint32_t operand(const peba1_gate& g, int q, int s, int32_t* slot, int16_t* sign) {
+    if (g.flags & PEBA1_IN_CONST(q)) {
+        *slot = -1;
+        *sign = 0;
+        uint32_t mu = g.in[q] ? kEighth : 0u - kEighth;
+        if (g.flags & PEBA1_IN_NEG(q)) mu = 0u - mu;
+        return (uint32_t)s * mu;
+    }
+    *slot = (int32_t)g.in[q];
+    *sign = (int16_t)((g.flags & PEBA1_IN_NEG(q)) ? -s : s);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int peba1_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ctx** out) {
+    if (!params || !out) return fail(PEBA1_EINVAL, "null argument");
+    *out = nullptr;
+    if (!params_supported(*params))
+        return fail(PEBA1_EINVAL, "unsupported parameter set (need N=1024, k=1, (l,Bgbit) in {(3,7),(2,10)}, ks t=8 base 4)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PEBA1_ENODEVICE, "no CUDA device (libpeba1_cuda has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(PEBA1_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(PEBA1_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    peba1_cuda_ctx* c = new (std::nothrow) peba1_cuda_ctx();
+    if (!c) return fail(PEBA1_ENOMEM, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->p = *params;
+    c->rows = 2 * params->l;
+    c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaEventCreate(&c->ev2));
+    static TwiddleTables tables;  // identical for every context
+    build_twiddle_tables(tables);
+    CU(cudaMemcpyToSymbol(c_tables, &tables, sizeof tables));
+    c->bkfft_bytes = (size_t)params->n * c->rows * 2 * kM * sizeof(double2);
+    c->ksk_bytes = (size_t)kN * params->ks_t * ((1 << params->ks_basebit) - 1) * c->pool_stride * sizeof(int32_t);
+    CU(cudaMalloc(&c->bkfft, c->bkfft_bytes));
+    CU(cudaMalloc(&c->ksk, c->ksk_bytes));
+    *out = c;
+    return 0;
+}
+
+int peba1_cuda_destroy(peba1_cuda_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->bkfft); cudaFree(c->ksk); cudaFree(c->pool); cudaFree(c->u); cudaFree(c->d_jobs); cudaFree(c->d_stage);
+    cudaFreeHost(c->h_jobs); cudaFreeHost(c->h_stage);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int peba1_cuda_set_stream(peba1_cuda_ctx* c, void* s) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int peba1_cuda_sync(peba1_cuda_ctx* c) {
+    if (int rc = use_device(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int peba1_cuda_load_bootstrap_key(peba1_cuda_ctx* c, const int32_t* bk_host) {
+    if (int rc = use_device(c)) return rc;
+    if (!bk_host) return fail(PEBA1_EINVAL, "null key");
+    const int64_t polys = (int64_t)c->p.n * c->rows * 2;
+    const size_t bytes = (size_t)polys * kN * sizeof(int32_t);
+    int32_t* d_bk = nullptr;
+    CU(cudaMalloc(&d_bk, bytes));
+    CU(cudaMemcpyAsync(d_bk, bk_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    constexpr int TEAMS = 4;
+    auto k = key_transform_kernel<TEAMS>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)team_smem_bytes(TEAMS)));
+    k<<<(unsigned)((polys + TEAMS - 1) / TEAMS), TEAMS * kTeam, team_smem_bytes(TEAMS), c->stream>>>(d_bk, c->rows, polys, c->bkfft);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(d_bk));
+    c->bk_loaded = true;
+    return 0;
+}
+
+int peba1_cuda_load_keyswitch_key(peba1_cuda_ctx* c, const int32_t* ksk_host) {
+    if (int rc = use_device(c)) return rc;
+    if (!ksk_host) return fail(PEBA1_EINVAL, "null key");
+    const int base = 1 << c->p.ks_basebit;
+    const size_t words = (size_t)kN * c->p.ks_t * base * (c->p.n + 1);
+    int32_t* d_src = nullptr;
+    CU(cudaMalloc(&d_src, words * sizeof(int32_t)));
+    CU(cudaMemcpyAsync(d_src, ksk_host, words * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    const int64_t rows_out = (int64_t)kN * c->p.ks_t * (base - 1);
+    ksk_pack_kernel<<<(unsigned)rows_out, 128, 0, c->stream>>>(d_src, c->p.n, base, c->pool_stride, rows_out, c->ksk);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(d_src));
+    c->ksk_loaded = true;
+    return 0;
+}
+
+int peba1_cuda_key_device_buffers(peba1_cuda_ctx* c, void** bkfft, uint64_t* bkfft_bytes, void** ksk, uint64_t* ksk_bytes) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    if (bkfft) *bkfft = c->bkfft;
+    if (bkfft_bytes) *bkfft_bytes = c->bkfft_bytes;
+    if (ksk) *ksk = c->ksk;
+    if (ksk_bytes) *ksk_bytes = c->ksk_bytes;
+    return 0;
+}
+
+int peba1_cuda_keys_mark_loaded(peba1_cuda_ctx* c) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    c->bk_loaded = c->ksk_loaded = true;
+    return 0;
+}
+
+int peba1_cuda_pool_reserve(peba1_cuda_ctx* c, int64_t slots) {
+    if (int rc = use_device(c)) return rc;
+    if (slots <= c->pool_slots) return 0;
+    if (slots > ((int64_t)1 << 31) - 1) return fail(PEBA1_EINVAL, "pool limited to 2^31-1 slots");
+    int32_t* np = nullptr;
+    const size_t bytes = (size_t)slots * c->pool_stride * sizeof(int32_t);
+    if (cudaMalloc(&np, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PEBA1_ENOMEM, "cannot allocate a pool of %lld slots (%zu bytes)", (long long)slots, bytes);
+    }
+    if (c->pool_slots > 0)
+        CU(cudaMemcpyAsync(np, c->pool, (size_t)c->pool_slots * c->pool_stride * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    pool_init_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(np, c->pool_stride, c->p.n, c->pool_slots, slots - c->pool_slots);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->pool) CU(cudaFree(c->pool));
+    c->pool = np;
+    c->pool_slots = slots;
+    return 0;
+}
+
+int peba1_cuda_pool_info(peba1_cuda_ctx* c, void** device_ptr, int64_t* stride_words, int64_t* capacity) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    if (device_ptr) *device_ptr = c->pool;
+    if (stride_words) *stride_words = c->pool_stride;
+    if (capacity) *capacity = c->pool_slots;
+    return 0;
+}
+
+static int check_slots(peba1_cuda_ctx* c, const int64_t* slots, int64_t first, int64_t count) {
+    if (count < 0) return fail(PEBA1_EINVAL, "negative count");
+    if (slots) {
+        for (int64_t i = 0; i < count; ++i)
+            if (slots[i] < 0 || slots[i] >= c->pool_slots) return fail(PEBA1_EINVAL, "slot %lld outside the pool (%lld slots)", (long long)slots[i], (long long)c->pool_slots);
+    } else if (first < 0 || first + count > c->pool_slots) {
+        return fail(PEBA1_EINVAL, "slot range [%lld, %lld) outside the pool (%lld slots)", (long long)first, (long long)(first + count), (long long)c->pool_slots);
+    }
+    return 0;
+}
+
+static int transfer(peba1_cuda_ctx* c, const int64_t* slots, int64_t first, int64_t count, const int32_t* h_in, int32_t* h_out) {
+    if (int rc = use_device(c)) return rc;
+    if (int rc = check_slots(c, slots, first, count)) return rc;
+    if (count == 0) return 0;
+    if ((h_in == nullptr) == (h_out == nullptr)) return fail(PEBA1_EINVAL, "null host buffer");
+    const int w = c->p.n + 1;
+    const int64_t chunk = 1 << 16;  // samples per staging round (165 MB)
+    for (int64_t off = 0; off < count; off += chunk) {
+        const int64_t m = std::min(chunk, count - off);
+        const size_t bytes = (size_t)m * w * sizeof(int32_t);
+        if (int rc = ensure_dev((void**)&c->d_stage, &c->d_stage_cap, bytes)) return rc;
+        int64_t* d_slots = nullptr;
+        if (slots) {
+            if (int rc = ensure_dev(&c->d_jobs, &c->d_jobs_cap, (size_t)m * sizeof(int64_t))) return rc;
+            d_slots = (int64_t*)c->d_jobs;
+            CU(cudaMemcpyAsync(d_slots, slots + off, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        }
+        if (h_in) {
+            CU(cudaMemcpyAsync(c->d_stage, h_in + (size_t)off * w, bytes, cudaMemcpyHostToDevice, c->stream));
+            scatter_kernel<<<(unsigned)m, 128, 0, c->stream>>>(c->pool, c->pool_stride, c->p.n, d_slots, first + off, c->d_stage);
+        } else {
+            gather_kernel<<<(unsigned)m, 128, 0, c->stream>>>(c->pool, c->pool_stride, c->p.n, d_slots, first + off, c->d_stage);
+            CU(cudaMemcpyAsync(h_out + (size_t)off * w, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CU(cudaGetLastError());
+        c->stats.launches++;
+        CU(cudaStreamSynchronize(c->stream));  // staging buffers are reused; host buffers may be pageable
+    }
+    return 0;
+}
+
+int peba1_cuda_upload(peba1_cuda_ctx* c, int64_t first, int64_t count, const int32_t* host) { return transfer(c, nullptr, first, count, host, nullptr); }
+int peba1_cuda_download(peba1_cuda_ctx* c, int64_t first, int64_t count, int32_t* host) { return transfer(c, nullptr, first, count, nullptr, host); }
+int peba1_cuda_upload_slots(peba1_cuda_ctx* c, const int64_t* slots, int64_t count, const int32_t* host) {
+    if (!slots) return fail(PEBA1_EINVAL, "null slots");
+    return transfer(c, slots, 0, count, host, nullptr);
+}
+int peba1_cuda_download_slots(peba1_cuda_ctx* c, const int64_t* slots, int64_t count, int32_t* host) {
+    if (!slots) return fail(PEBA1_EINVAL, "null slots");
+    return transfer(c, slots, 0, count, nullptr, host);
+}
+
+int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) {
+    if (int rc = use_device(c)) return rc;
+    if (count < 0 || (count > 0 && !gates)) return fail(PEBA1_EINVAL, "bad gate list");
+    if (!c->bk_loaded || !c->ksk_loaded) return fail(PEBA1_ENOKEY, "keys are not loaded");
+    // validate everything before launching anything
+    for (int64_t i = 0; i < count; ++i) {
+        const peba1_gate& g = gates[i];
+        if (g.op < 0 || g.op > PEBA1_OP_MUX) return fail(PEBA1_EINVAL, "gate %lld: unknown op %d", (long long)i, g.op);
+        const int nin = g.op == PEBA1_OP_MUX ? 3 : 2;
+        for (int q = 0; q < nin; ++q) {
+            if (g.flags & PEBA1_IN_CONST(q)) {
+                if (g.in[q] != 0 && g.in[q] != 1) return fail(PEBA1_EINVAL, "gate %lld: constant operand must be 0 or 1", (long long)i);
+            } else if (g.in[q] < 0 || g.in[q] >= c->pool_slots) {
+                return fail(PEBA1_EINVAL, "gate %lld: input slot %lld outside the pool (%lld slots)", (long long)i, (long long)g.in[q], (long long)c->pool_slots);
+            }
+        }
+        if (g.out < 0 || g.out >= c->pool_slots) return fail(PEBA1_EINVAL, "gate %lld: output slot %lld outside the pool", (long long)i, (long long)g.out);
+    }
+    int64_t done = 0;
+    while (done < count) {
+        // take gates until the PBS budget of one launch is reached
+        int64_t npbs = 0, m = 0;
+        while (done + m < count) {
+            const int need = gates[done + m].op == PEBA1_OP_MUX ? 2 : 1;
+            if (m > 0 && npbs + need > c->max_pbs_per_launch) break;
+            npbs += need;
+            ++m;
+        }
+        const size_t jb = (size_t)npbs * sizeof(PbsJob), kb = (size_t)m * sizeof(KsJob);
+        const size_t kb_off = (jb + 255) / 256 * 256;
+        // a previous chunk may still be reading the pinned job list
+        if (done > 0) CU(cudaStreamSynchronize(c->stream));
+        if (int rc = ensure_pinned(&c->h_jobs, &c->h_jobs_cap, kb_off + kb)) return rc;
+        if (int rc = ensure_dev(&c->d_jobs, &c->d_jobs_cap, kb_off + kb)) return rc;
+        if (c->u_cap < npbs) {
+            if (c->u) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->u)); c->u = nullptr; c->u_cap = 0; }
+            const int64_t want = std::max<int64_t>(npbs, 4096);
+            if (cudaMalloc(&c->u, (size_t)want * kUStride * sizeof(int32_t)) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(PEBA1_ENOMEM, "cannot allocate the extracted-sample workspace for %lld bootstraps", (long long)want);
+            }
+            c->u_cap = want;
+        }
+        PbsJob* pj = (PbsJob*)c->h_jobs;
+        KsJob* kj = (KsJob*)((char*)c->h_jobs + kb_off);
+        int64_t ip = 0;
+        for (int64_t i = 0; i < m; ++i) {
+            const peba1_gate& g = gates[done + i];
+            KsJob& k = kj[i];
+            k.pad = 0;
+            k.out_slot = g.out;
+            if (g.op == PEBA1_OP_MUX) {
+                // u1 = PBS(-1/8 + a + b), u2 = PBS(-1/8 - a + c), out = KS((0,1/8) + u1 + u2)
+                PbsJob& j1 = pj[ip];
+                PbsJob& j2 = pj[ip + 1];
+                uint32_t c1 = 0u - kEighth, c2 = 0u - kEighth;
+                c1 += operand(g, 0, 1, &j1.in0, &j1.s0);
+                c1 += operand(g, 1, 1, &j1.in1, &j1.s1);
+                c2 += operand(g, 0, -1, &j2.in0, &j2.s0);
+                c2 += operand(g, 2, 1, &j2.in1, &j2.s1);
+                j1.c0 = (int32_t)c1;
+                j2.c0 = (int32_t)c2;
+                k.u0 = (int32_t)ip;
+                k.u1 = (int32_t)ip + 1;
+                k.c0 = (int32_t)kEighth;
+                ip += 2;
+            } else {
+                int c0, sa, sb;
+                gate_consts(g.op, &c0, &sa, &sb);
+                PbsJob& j = pj[ip];
+                uint32_t cc = (uint32_t)c0 * kEighth;
+                cc += operand(g, 0, sa, &j.in0, &j.s0);
+                cc += operand(g, 1, sb, &j.in1, &j.s1);
+                j.c0 = (int32_t)cc;
+                k.u0 = (int32_t)ip;
+                k.u1 = -1;
+                k.c0 = 0;
+                ip += 1;
+            }
+        }
+        CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, kb_off + kb, cudaMemcpyHostToDevice, c->stream));
+        if (int rc = launch_pbs(c, c->pool, c->pool_stride, (const PbsJob*)c->d_jobs, npbs, c->u)) return rc;
+        if (int rc = launch_ks(c, c->u, (const KsJob*)((char*)c->d_jobs + kb_off), m, c->pool)) return rc;
+        if (int rc = collect_timing(c, true, true)) return rc;
+        done += m;
+    }
+    // the pinned job list is reused by the next call
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int peba1_cuda_gate_batch(peba1_cuda_ctx* c, int32_t op, const int64_t* in0, const int64_t* in1, const int64_t* in2, const int64_t* out, int64_t count) {
+    if (count < 0 || (count > 0 && (!in0 || !in1 || !out))) return fail(PEBA1_EINVAL, "null slot array");
+    if (op == PEBA1_OP_MUX && count > 0 && !in2) return fail(PEBA1_EINVAL, "MUX needs three operands");
+    std::vector<peba1_gate> g((size_t)count);
+    for (int64_t i = 0; i < count; ++i) {
+        g[i].op = op;
+        g[i].flags = 0;
+        g[i].in[0] = in0[i];
+        g[i].in[1] = in1[i];
+        g[i].in[2] = in2 ? in2[i] : 0;
+        g[i].out = out[i];
+    }
+    return peba1_cuda_gates(c, g.data(), count);
+}
+
+int peba1_cuda_gate_batch_host(peba1_cuda_ctx* c, int32_t op, const int32_t* ca, const int32_t* cb, const int32_t* cc, int32_t* out, int64_t count) {
+    if (count < 0 || (count > 0 && (!ca || !cb || !out))) return fail(PEBA1_EINVAL, "null host buffer");
+    const bool mux = op == PEBA1_OP_MUX;
+    if (mux && count > 0 && !cc) return fail(PEBA1_EINVAL, "MUX needs three operands");
+    if (count == 0) return 0;
+    const int nin = mux ? 3 : 2;
+    if (int rc = peba1_cuda_pool_reserve(c, (nin + 1) * count)) return rc;
+    if (int rc = peba1_cuda_upload(c, 0, count, ca)) return rc;
+    if (int rc = peba1_cuda_upload(c, count, count, cb)) return rc;
+    if (mux) if (int rc = peba1_cuda_upload(c, 2 * count, count, cc)) return rc;
+    std::vector<peba1_gate> g((size_t)count);
+    for (int64_t i = 0; i < count; ++i) {
+        g[i].op = op;
+        g[i].flags = 0;
+        g[i].in[0] = i;
+        g[i].in[1] = count + i;
+        g[i].in[2] = mux ? 2 * count + i : 0;
+        g[i].out = nin * count + i;
+    }
+    if (int rc = peba1_cuda_gates(c, g.data(), count)) return rc;
+    return peba1_cuda_download(c, nin * count, count, out);
+}
+
+int peba1_cuda_linear(peba1_cuda_ctx* c, const int64_t* in, const int32_t* sign, const int32_t* cst, const int64_t* out, int64_t count) {
+    if (int rc = use_device(c)) return rc;
+    if (count < 0 || (count > 0 && (!in || !sign || !cst || !out))) return fail(PEBA1_EINVAL, "null argument");
+    if (count == 0) return 0;
+    for (int64_t i = 0; i < count; ++i) {
+        if (in[i] >= c->pool_slots) return fail(PEBA1_EINVAL, "input slot outside the pool");
+        if (out[i] < 0 || out[i] >= c->pool_slots) return fail(PEBA1_EINVAL, "output slot outside the pool");
+    }
+    const size_t a = (size_t)count * sizeof(int64_t), b = (size_t)count * sizeof(int32_t);
+    if (int rc = ensure_dev(&c->d_jobs, &c->d_jobs_cap, 2 * a + 2 * b)) return rc;
+    char* d = (char*)c->d_jobs;
+    CU(cudaMemcpyAsync(d, in, a, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + a, out, a, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + 2 * a, sign, b, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d + 2 * a + b, cst, b, cudaMemcpyHostToDevice, c->stream));
+    linear_kernel<<<(unsigned)count, 128, 0, c->stream>>>(c->pool, c->pool_stride, c->p.n, (const int64_t*)d, (const int32_t*)(d + 2 * a), (const int32_t*)(d + 2 * a + b), (const int64_t*)(d + a));
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int peba1_cuda_bootstrap_woks_host(peba1_cuda_ctx* c, const int32_t* in, int32_t* out_extracted, int64_t count) {
+    if (int rc = use_device(c)) return rc;
+    if (count < 0 || (count > 0 && (!in || !out_extracted))) return fail(PEBA1_EINVAL, "null host buffer");
+    if (!c->bk_loaded) return fail(PEBA1_ENOKEY, "bootstrapping key is not loaded");
+    if (count == 0) return 0;
+    const int w = c->p.n + 1;
+    int32_t *d_in = nullptr, *d_u = nullptr, *d_dense = nullptr;
+    PbsJob* d_j = nullptr;
+    CU(cudaMalloc(&d_in, (size_t)count * w * sizeof(int32_t)));
+    CU(cudaMalloc(&d_u, (size_t)count * kUStride * sizeof(int32_t)));
+    CU(cudaMalloc(&d_dense, (size_t)count * (kN + 1) * sizeof(int32_t)));
+    CU(cudaMalloc(&d_j, (size_t)count * sizeof(PbsJob)));
+    std::vector<PbsJob> jobs((size_t)count);
+    for (int64_t i = 0; i < count; ++i) jobs[i] = PbsJob{(int32_t)i, -1, 0, 1, 0};
+    CU(cudaMemcpyAsync(d_in, in, (size_t)count * w * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_j, jobs.data(), (size_t)count * sizeof(PbsJob), cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_pbs(c, d_in, w, d_j, count, d_u)) return rc;
+    u_unpad_kernel<<<(unsigned)count, 128, 0, c->stream>>>(d_u, d_dense, 1);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    CU(cudaMemcpyAsync(out_extracted, d_dense, (size_t)count * (kN + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_in); cudaFree(d_u); cudaFree(d_dense); cudaFree(d_j);
+    return 0;
+}
+
+int peba1_cuda_keyswitch_host(peba1_cuda_ctx* c, const int32_t* in_extracted, int32_t* out, int64_t count) {
+    if (int rc = use_device(c)) return rc;
+    if (count < 0 || (count > 0 && (!in_extracted || !out))) return fail(PEBA1_EINVAL, "null host buffer");
+    if (!c->ksk_loaded) return fail(PEBA1_ENOKEY, "keyswitch key is not loaded");
+    if (count == 0) return 0;
+    if (int rc = peba1_cuda_pool_reserve(c, count)) return rc;
+    int32_t *d_u = nullptr, *d_dense = nullptr;
+    KsJob* d_j = nullptr;
+    CU(cudaMalloc(&d_u, (size_t)count * kUStride * sizeof(int32_t)));
+    CU(cudaMalloc(&d_dense, (size_t)count * (kN + 1) * sizeof(int32_t)));
+    CU(cudaMalloc(&d_j, (size_t)count * sizeof(KsJob)));
+    std::vector<KsJob> jobs((size_t)count);
+    for (int64_t i = 0; i < count; ++i) jobs[i] = KsJob{(int32_t)i, -1, 0, 0, i};
+    CU(cudaMemcpyAsync(d_dense, in_extracted, (size_t)count * (kN + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_j, jobs.data(), (size_t)count * sizeof(KsJob), cudaMemcpyHostToDevice, c->stream));
+    u_unpad_kernel<<<(unsigned)count, 128, 0, c->stream>>>(d_u, d_dense, 0);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
+    if (int rc = launch_ks(c, d_u, d_j, count, c->pool)) return rc;
+    if (int rc = collect_timing(c, false, true)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_u); cudaFree(d_dense); cudaFree(d_j);
+    return peba1_cuda_download(c, 0, count, out);
+}
+
+int peba1_cuda_enable_timing(peba1_cuda_ctx* c, int enable) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    c->timing = enable != 0;
+    return 0;
+}
+int peba1_cuda_get_stats(peba1_cuda_ctx* c, peba1_cuda_stats* out) {
+    if (!c || !out) return fail(PEBA1_EINVAL, "null argument");
+    *out = c->stats;
+    return 0;
+}
+int peba1_cuda_reset_stats(peba1_cuda_ctx* c) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    c->stats = peba1_cuda_stats{};
+    return 0;
+}
+
+int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* c, double* tflops) {
+    if (int rc = use_device(c)) return rc;
+    if (!tflops) return fail(PEBA1_EINVAL, "null argument");
+    const int threads = 256, blocks = c->sm_count * 8, iters = 1 << 14;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)threads * blocks * sizeof(double)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(c->ev0, c->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, c->stream>>>(d, iters);
+        CU(cudaEventRecord(c->ev1, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    CU(cudaFree(d));
+    c->stats.launches += 4;
+    *tflops = 2.0 * 8 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;
+    return 0;
+}
+
+int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return fail(PEBA1_EINVAL, "null argument");
+    if (!strcmp(name, "teams_per_cta")) {
+        if (value == 0) value = 4;
+        if (value != 1 && value != 2 && value != 3 && value != 4 && value != 6) return fail(PEBA1_EINVAL, "teams_per_cta must be 1, 2, 3, 4 or 6");
+        c->teams_per_cta = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "max_pbs_per_launch")) {
+        if (value == 0) value = 1 << 18;
+        if (value < 1) return fail(PEBA1_EINVAL, "max_pbs_per_launch must be positive");
+        c->max_pbs_per_launch = value;
+        return 0;
+    }
+    return fail(PEBA1_EINVAL, "unknown option '%s'", name);
+}
+
+}  // extern "C"

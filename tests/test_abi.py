@@ -1,0 +1,64 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/peba1_cuda.h declares,
+and fails loudly (no fallback) without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import peba1_b200 as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "peba1_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(peba1_cuda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbol_list_matches_binding():
+    assert _header_symbols() == sorted(P.DECLARED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = P.load_library()
+    for s in _header_symbols():
+        assert hasattr(L, s), f"libpeba1_cuda.so does not export {s}"
+
+
+def test_struct_layouts():
+    assert C.sizeof(P.Gate) == 40
+    assert C.sizeof(P.Params) == 28
+    from peba1_b200.cuda import GATE_DTYPE
+    assert GATE_DTYPE.itemsize == 40 and GATE_DTYPE.fields["out"][1] == 32
+
+
+def test_no_device_fails_loudly():
+    L = P.load_library()
+    if L.peba1_cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(P.PEBA1Error) as ei:
+        P.Engine()
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_bad_params_rejected():
+    L = P.load_library()
+    h = C.c_void_p()
+    bad = P.Params(630, 2048, 1, 3, 7, 8, 2)
+    assert L.peba1_cuda_create(0, C.byref(bad), C.byref(h)) == -1
+    assert b"unsupported parameter set" in L.peba1_cuda_last_error()
+    assert L.peba1_cuda_create(0, None, C.byref(h)) == -1
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through the oracle (test infrastructure only)."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "peba1_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                if f == "emu_team.cu":
+                    continue
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "tfhe_oracle" not in txt and "pyoracle" not in txt, os.path.join(dirpath, f)

@@ -1,0 +1,140 @@
+"""GPU parity tests: the CUDA path through the C ABI (include/peba1_cuda.h) against the oracle, bit-exact.
+
+Everything here runs on the B200 box (`-m gpu`); nothing reads /root/reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from test_oracle import TRUTH
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "gates_seed42.npz")
+
+
+def test_native_library_is_loaded(engine):
+    import peba1_b200 as P
+    maps = open("/proc/self/maps").read()
+    assert "libpeba1_cuda.so" in maps
+    assert P.load_library().peba1_cuda_device_count() >= 1
+
+
+def test_golden_pieces(engine):
+    """bootstrap-without-keyswitch and keyswitch alone reproduce the exact-integer golden vectors."""
+    g = np.load(GOLDEN)
+    u = engine.bootstrap_woks_host(g["pbs_in"][None, :])
+    assert np.array_equal(u[0], g["pbs_out"])
+    out = engine.keyswitch_host(g["pbs_out"][None, :])
+    assert np.array_equal(out[0], g["ks_out"])
+
+
+def test_golden_gates_all_ops(engine, keys):
+    g = np.load(GOLDEN)
+    for op in TRUTH:
+        out = engine.gate_batch_host(op, g["ca"], g["cb"])
+        assert np.array_equal(out, g["out_" + op]), op
+    out = engine.gate_batch_host("MUX", g["cs"], g["cx"], g["cy"])
+    assert np.array_equal(out, g["out_MUX"])
+
+
+@pytest.mark.parametrize("op", ["NAND", "XOR", "MUX"])
+def test_random_batch_matches_oracle(engine, oracle, keys, op):
+    """256 random gates per op vs the FFT-form oracle (itself pinned to the exact form in test_oracle.py)."""
+    n = 256
+    rng = np.random.default_rng(100 + len(op))
+    a, b, c = (rng.integers(0, 2, size=n) for _ in range(3))
+    ca, cb, cc = keys.encrypt(a, 31), keys.encrypt(b, 32), keys.encrypt(c, 33)
+    if op == "MUX":
+        got = engine.gate_batch_host(op, ca, cb, cc)
+        want = keys.gate_batch(op, ca, cb, cc, threads=os.cpu_count() or 1)
+        bits = np.where(a == 1, b, c)
+    else:
+        got = engine.gate_batch_host(op, ca, cb)
+        want = keys.gate_batch(op, ca, cb, threads=os.cpu_count() or 1)
+        bits = np.array([TRUTH[op](int(x), int(y)) for x, y in zip(a, b)])
+    assert np.array_equal(got, want)
+    assert np.array_equal(keys.decrypt(got), bits)
+
+
+def test_ragged_and_empty_batches(engine, keys):
+    assert engine.gate_batch_host("AND", np.zeros((0, 631), np.int32), np.zeros((0, 631), np.int32)).shape == (0, 631)
+    for n in (1, 3, 5, 7):   # not a multiple of the teams per CTA
+        a = np.arange(n) % 2
+        b = (np.arange(n) // 2) % 2
+        ca, cb = keys.encrypt(a, 41 + n), keys.encrypt(b, 51 + n)
+        got = engine.gate_batch_host("OR", ca, cb)
+        assert np.array_equal(got, keys.gate_batch("OR", ca, cb, threads=4))
+
+
+def test_operand_flags_and_aliasing(engine, oracle, keys):
+    """NEG / CONST operand modifiers (bootsNOT / bootsCONSTANT folded into the gate) and out == in aliasing."""
+    from peba1_b200.cuda import make_gates, IN_NEG, IN_CONST
+    a = np.array([0, 1, 0, 1]); b = np.array([0, 0, 1, 1])
+    ca, cb = keys.encrypt(a, 61), keys.encrypt(b, 62)
+    engine.reserve(64)
+    engine.upload(0, ca); engine.upload(4, cb)
+    # gate i: AND(NOT a_i, b_i) -> slot 8+i
+    g1 = make_gates("AND", np.arange(4), 4 + np.arange(4), 8 + np.arange(4), flags=IN_NEG(0))
+    # gate i: XOR(a_i, const 1) -> written over a_i itself (aliasing, reference Math.cpp:84,272)
+    g2 = make_gates("XOR", np.arange(4), np.ones(4, dtype=np.int64), np.arange(4), flags=IN_CONST(1))
+    engine.gates(np.concatenate([g1, g2]))
+    got1, got2 = engine.download(8, 4), engine.download(0, 4)
+    nota = np.stack([-ca[i] for i in range(4)]).astype(np.int32)
+    want1 = keys.gate_batch("AND", nota, cb, threads=4)
+    t1 = np.stack([keys.trivial(1)] * 4)
+    want2 = keys.gate_batch("XOR", ca, t1, threads=4)
+    assert np.array_equal(got1, want1) and np.array_equal(got2, want2)
+    assert keys.decrypt(got1).tolist() == ((1 - a) & b).tolist()
+    assert keys.decrypt(got2).tolist() == (1 - a).tolist()
+
+
+def test_never_written_slot_is_trivial_false(engine, keys):
+    """fresh pool slots read as (a=0, b=-1/8)."""
+    _, _, cap = engine.pool_info()
+    engine.reserve(cap + 16)
+    fresh = engine.download(cap, 16)
+    assert not fresh[:, :-1].any() and np.all(fresh[:, -1] == -(1 << 29))
+    assert keys.decrypt(fresh).tolist() == [0] * 16
+
+
+def test_linear_ops(engine, keys):
+    """bootsNOT / bootsCOPY / bootsCONSTANT on device slots."""
+    ct = keys.encrypt([1, 0], 71)
+    engine.reserve(32)
+    engine.upload(0, ct)
+    mu = 1 << 29
+    engine.linear([0, 1, -1, -1], [-1, 1, 0, 0], [0, 0, mu, -mu], [10, 11, 12, 13])
+    got = engine.download(10, 4)
+    assert np.array_equal(got[0], (-ct[0]).astype(np.int32)) and np.array_equal(got[1], ct[1])
+    assert np.array_equal(got[2], keys.trivial(1)) and np.array_equal(got[3], keys.trivial(0))
+
+
+def test_errors(engine):
+    import peba1_b200 as P
+    from peba1_b200.cuda import make_gates
+    _, _, cap = engine.pool_info()
+    with pytest.raises(P.PEBA1Error):
+        engine.gates(make_gates("AND", [0], [cap + 5], [0]))
+    with pytest.raises(P.PEBA1Error):
+        engine.gates(make_gates(99, [0], [0], [0]))
+    with pytest.raises(P.PEBA1Error):
+        engine.download(cap, 1)
+
+
+def test_size_independent_properties_full_batch(engine, keys):
+    """BASELINE config 2 size (16,384 gates): properties that need no oracle run.
+    NAND(x, x) == NOT x after decryption; XOR(x, y) then XOR(., y) gives x back; all phases within 2^-5 of +-1/8."""
+    n = 16384
+    rng = np.random.default_rng(5)
+    x, y = rng.integers(0, 2, size=n), rng.integers(0, 2, size=n)
+    cx, cy = keys.encrypt(x, 81), keys.encrypt(y, 82)
+    nx = engine.gate_batch_host("NAND", cx, cx)
+    assert np.array_equal(keys.decrypt(nx), 1 - x)
+    z = engine.gate_batch_host("XOR", cx, cy)
+    back = engine.gate_batch_host("XOR", z, cy)
+    assert np.array_equal(keys.decrypt(back), x)
+    ph = keys.phase(back).astype(np.float64) / 2.0**32
+    assert np.all(np.abs(np.abs(ph) - 0.125) < 2.0**-5)
+    # determinism: the same launch twice gives identical words
+    assert np.array_equal(z, engine.gate_batch_host("XOR", cx, cy))
