@@ -1,0 +1,78 @@
+/*
+ * include/peba1_host.h — extensions of the TFHE-compatible front end (libpeba1_tfhe.so) beyond upstream's API:
+ * flush control, batching of many circuit instances, statistics, and raw access to samples and keys for bindings
+ * and tests.  Everything is plain C ABI.
+ */
+#ifndef PEBA1_HOST_H
+#define PEBA1_HOST_H
+
+#include <stdint.h>
+#include "tfhe/tfhe_core.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* GPU used by contexts created after this call (default: $PEBA1_DEVICE, else $LOCAL_RANK, else 0). */
+void peba1_host_set_device(int device);
+
+/* TEST HOOK — not a fallback.  Engines created after this call hand the four device operations of the recorder to the
+   given table instead of libpeba1_cuda, so the CPU test-suite can check the schedule (levels, widths, slot reuse,
+   aliasing) with a bit-level simulator.  Nothing in the product installs a backend; without one (the default) the
+   first gate needs a CUDA device and aborts otherwise. */
+typedef struct {
+    void* user;
+    int (*reserve)(void* user, int64_t slots);
+    int (*upload_slots)(void* user, const int64_t* slots, int64_t count, const int32_t* words);
+    int (*download)(void* user, int64_t slot, int32_t* words);
+    int (*gates)(void* user, const void* gates /* const peba1_gate* */, int64_t count);
+} peba1_test_backend;
+void peba1_host_set_test_backend(const peba1_test_backend* backend);
+
+/* Executes every recorded gate: one peba1_cuda_gates() call (2 kernel launches) per circuit level. */
+void peba1_flush(void);
+/* While a batch is open, Math.h routines do not flush on exit, so many instances share each level's launch. */
+void peba1_batch_begin(void);
+void peba1_batch_end(void); /* closes the batch and flushes when the outermost one ends */
+/* eager = 1 (default): the outermost Math.h routine flushes before returning, which keeps the reference's per-routine
+   wall-clock timings (src/main.cpp:310-312) meaningful.  eager = 0: flush only on decrypt / peba1_flush. */
+void peba1_set_eager(int eager);
+
+typedef struct {
+    uint64_t gates;        /* bootstrapped gates recorded (MUX counts once) */
+    uint64_t pbs;          /* bootstraps those gates need (MUX = 2) */
+    uint64_t linear;       /* NOT / COPY / CONSTANT calls (never launched: resolved as aliases) */
+    uint64_t levels;       /* circuit levels executed = batched launch pairs */
+    uint64_t flushes;
+    uint64_t max_level_width;
+    uint64_t uploads, downloads; /* ciphertexts moved host->device / device->host */
+    uint64_t live_slots, peak_slots;
+    double flush_seconds;  /* wall time spent inside flushes */
+} peba1_host_stats;
+void peba1_get_stats(peba1_host_stats* out);
+void peba1_reset_stats(void);
+
+/* Raw sample access (n+1 words: a[0..n-1], b).  _get flushes if the value is still pending. */
+int32_t peba1_sample_words(const TFheGateBootstrappingParameterSet* params);
+void peba1_sample_get(const LweSample* sample, const TFheGateBootstrappingCloudKeySet* bk, int32_t* words);
+void peba1_sample_set(LweSample* sample, const int32_t* words);
+LweSample* peba1_sample_at(LweSample* array, int32_t index); /* &array[index] for bindings */
+
+/* Deterministic key generation (new_random_gate_bootstrapping_secret_keyset uses the global generator). */
+TFheGateBootstrappingSecretKeySet* peba1_new_secret_keyset_seeded(const TFheGateBootstrappingParameterSet* params, uint64_t seed);
+/* A keyset around caller-provided key arrays (copied): lwe_key[n], tlwe_key[N] may be NULL for a cloud-only use. */
+TFheGateBootstrappingSecretKeySet* peba1_new_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params,
+                                                                const int32_t* lwe_key, const int32_t* tlwe_key,
+                                                                const int32_t* bk, const int32_t* ksk);
+const int32_t* peba1_keyset_bk(const TFheGateBootstrappingCloudKeySet* bk);   /* [n][2l][2][N] */
+const int32_t* peba1_keyset_ksk(const TFheGateBootstrappingCloudKeySet* bk);  /* [N][t][2^basebit][n+1] */
+/* Batch encryption with an explicit seed: bits[count] -> words[count][n+1]. */
+void peba1_encrypt_bits(const TFheGateBootstrappingSecretKeySet* key, const int32_t* bits, int64_t count, uint64_t seed, int32_t* words);
+void peba1_decrypt_words(const TFheGateBootstrappingSecretKeySet* key, const int32_t* words, int64_t count, int32_t* bits);
+/* The libpeba1_cuda context behind a cloud key (created on first use); NULL without a device. */
+void* peba1_cuda_context_of(const TFheGateBootstrappingCloudKeySet* bk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,695 @@
+// tfhe_front.cpp — libpeba1_tfhe.so: the TFHE gate-bootstrapping API of include/tfhe/*.h as a recording front end
+// of libpeba1_cuda (see recorder.hpp), plus host-side key generation and encryption/decryption.
+//
+// What stays on the host (north_star: "keygen still runs on the host"): parameter sets, LWE/TLWE/bootstrapping/
+// keyswitch key generation, bootsSymEncrypt / bootsSymDecrypt (§3.4).  What goes to the GPU: every
+// bootstrapped gate, batched per circuit level.  The integer bootstrapping key is uploaded once and transformed on
+// the device.  No CPU implementation of the gates exists in this library: without a device the first gate aborts.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <random>
+#include <thread>
+#include <vector>
+
+#include "../../include/tfhe/tfhe.h"
+#include "recorder.hpp"
+
+namespace peba1 {
+
+[[noreturn]] static void die(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    fprintf(stderr, "peba1: fatal: ");
+    vfprintf(stderr, fmt, ap);
+    fprintf(stderr, "\n");
+    va_end(ap);
+    abort();  // upstream TFHE aborts on fatal errors too
+}
+
+// ------------------------------------------------------------------------------------------------ key material
+}  // namespace peba1
+
+struct peba1_key_material {
+    TFheGateBootstrappingParameterSet params;
+    std::vector<int32_t> lwe_key, tlwe_key, bk, ksk;
+    peba1::Engine* engine = nullptr;
+};
+
+namespace peba1 {
+
+struct Wire {
+    int64_t slot = -1;   // device pool slot while the value is materialised
+    int32_t refs = 0;
+    int32_t level = 0;   // 0: available (materialised or queued for upload); >0: produced by a pending node
+    int32_t eng = -1;
+    int32_t next_free = -1;
+};
+
+struct Engine {
+    int index = 0;
+    peba1_key_material* km = nullptr;
+    peba1_cuda_ctx* ctx = nullptr;          // null when a test backend is installed
+    const peba1_test_backend* tb = nullptr;  // see peba1_host_set_test_backend (never set by the product)
+    int words = 0;
+    std::vector<std::vector<peba1_gate>> levels;  // pending nodes; in[]/out hold WIRE ids (or constant bits)
+    std::vector<int64_t> up_wires;
+    std::vector<int32_t> up_words;
+    std::vector<int64_t> free_slots;
+    int64_t next_slot = 0, capacity = 0;
+    std::vector<peba1_gate> scratch;
+    int routine_depth = 0;
+};
+
+static std::recursive_mutex g_mu;
+static std::vector<Wire> g_wires(2);  // wire 0 unused, wire 1 = constant false
+static int32_t g_free_wire = -1;
+static std::vector<Engine*> g_engines;
+static Engine* g_current = nullptr;
+static int g_device = -1;
+static int g_batch_depth = 0;
+static bool g_eager = true;
+static peba1_host_stats g_stats{};
+static const peba1_test_backend* g_test_backend = nullptr;
+
+// The four engine operations the recorder needs.  The product path is libpeba1_cuda; the table exists only so the
+// CPU test-suite can observe the schedule (tests/ installs a bit-level simulator).
+static int be_reserve(Engine* e, int64_t slots);
+static int be_upload_slots(Engine* e, const int64_t* slots, int64_t count, const int32_t* words);
+static int be_download(Engine* e, int64_t slot, int32_t* words);
+static int be_gates(Engine* e, const peba1_gate* gates, int64_t count);
+
+static int pick_device() {
+    if (g_device >= 0) return g_device;
+    if (const char* s = getenv("PEBA1_DEVICE")) return atoi(s);
+    if (const char* s = getenv("LOCAL_RANK")) return atoi(s);
+    return 0;
+}
+
+#define CUCHK(e, call)                                                              \
+    do {                                                                            \
+        int rc_ = (call);                                                           \
+        if (rc_ != 0) die("%s failed (%d): %s", #call, rc_, peba1_cuda_last_error()); \
+    } while (0)
+
+Engine* engine_of(const TFheGateBootstrappingCloudKeySet* bk) {
+    if (!bk || !bk->material) die("gate called with a null cloud key");
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    peba1_key_material* km = bk->material;
+    if (!km->engine) {
+        Engine* e = new Engine();
+        e->km = km;
+        e->index = (int)g_engines.size();
+        e->words = km->params.n + 1;
+        e->tb = g_test_backend;
+        if (!e->tb) {
+            peba1_cuda_params p{km->params.n, km->params.N, km->params.k, km->params.l, km->params.Bgbit,
+                                km->params.ks_t, km->params.ks_basebit};
+            CUCHK(e, peba1_cuda_create(pick_device(), &p, &e->ctx));
+            CUCHK(e, peba1_cuda_load_bootstrap_key(e->ctx, km->bk.data()));
+            CUCHK(e, peba1_cuda_load_keyswitch_key(e->ctx, km->ksk.data()));
+        }
+        g_engines.push_back(e);
+        km->engine = e;
+    }
+    g_current = km->engine;
+    return km->engine;
+}
+Engine* current_engine() { return g_current; }
+
+static int be_reserve(Engine* e, int64_t slots) {
+    return e->tb ? e->tb->reserve(e->tb->user, slots) : peba1_cuda_pool_reserve(e->ctx, slots);
+}
+static int be_upload_slots(Engine* e, const int64_t* slots, int64_t count, const int32_t* words) {
+    return e->tb ? e->tb->upload_slots(e->tb->user, slots, count, words)
+                 : peba1_cuda_upload_slots(e->ctx, slots, count, words);
+}
+static int be_download(Engine* e, int64_t slot, int32_t* words) {
+    return e->tb ? e->tb->download(e->tb->user, slot, words) : peba1_cuda_download(e->ctx, slot, 1, words);
+}
+static int be_gates(Engine* e, const peba1_gate* gates, int64_t count) {
+    return e->tb ? e->tb->gates(e->tb->user, gates, count) : peba1_cuda_gates(e->ctx, gates, count);
+}
+
+static int64_t new_wire(Engine* e, int level) {
+    int64_t id;
+    if (g_free_wire >= 0) {
+        id = g_free_wire;
+        g_free_wire = g_wires[id].next_free;
+    } else {
+        id = (int64_t)g_wires.size();
+        g_wires.emplace_back();
+    }
+    Wire& w = g_wires[id];
+    w.slot = -1;
+    w.refs = 1;
+    w.level = level;
+    w.eng = e->index;
+    w.next_free = -1;
+    return id;
+}
+
+static void unref_wire(int64_t id) {
+    Wire& w = g_wires[id];
+    if (--w.refs > 0) return;
+    if (w.refs < 0) die("wire %lld released twice", (long long)id);
+    Engine* e = g_engines[w.eng];
+    if (w.slot >= 0) {
+        e->free_slots.push_back(w.slot);
+        g_stats.live_slots--;
+    }
+    w.slot = -1;
+    w.next_free = g_free_wire;
+    g_free_wire = (int32_t)id;
+}
+
+void retain(Handle h) {
+    if (h == 0 || is_const(h)) return;
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    g_wires[h >> 1].refs++;
+}
+void release(Handle h) {
+    if (h == 0 || is_const(h)) return;
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    unref_wire((int64_t)(h >> 1));
+}
+
+static int64_t alloc_slot(Engine* e) {
+    g_stats.live_slots++;
+    if (g_stats.live_slots > g_stats.peak_slots) g_stats.peak_slots = g_stats.live_slots;
+    if (!e->free_slots.empty()) {
+        int64_t s = e->free_slots.back();
+        e->free_slots.pop_back();
+        return s;
+    }
+    return e->next_slot++;
+}
+static void ensure_capacity(Engine* e) {
+    if (e->next_slot <= e->capacity) return;
+    int64_t want = std::max<int64_t>(e->next_slot, std::max<int64_t>(4096, e->capacity * 2));
+    CUCHK(e, be_reserve(e, want));
+    e->capacity = want;
+}
+
+// fills operand q of a node from a handle; returns the operand's level
+static int set_operand(peba1_gate& g, int q, Handle h) {
+    if (h == 0) die("internal: host handle used as a gate operand");
+    if (is_const(h)) {
+        g.flags |= PEBA1_IN_CONST(q);
+        g.in[q] = (int64_t)(h & 1);
+        return 0;
+    }
+    g.in[q] = (int64_t)(h >> 1);
+    if (h & 1) g.flags |= PEBA1_IN_NEG(q);
+    Wire& w = g_wires[h >> 1];
+    w.refs++;  // the pending node holds its operands
+    return w.level;
+}
+
+static Handle push_node(Engine* e, peba1_gate& g, int level) {
+    const int64_t out = new_wire(e, level);  // the node's own reference, dropped after execution
+    g_wires[out].refs++;                     // the caller's reference
+    g.out = out;
+    if ((int)e->levels.size() < level) e->levels.resize(level);
+    e->levels[level - 1].push_back(g);
+    return (Handle)out << 1;
+}
+
+Handle record_gate(Engine* e, int op, Handle a, Handle b) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    peba1_gate g{};
+    g.op = op;
+    const int la = set_operand(g, 0, a), lb = set_operand(g, 1, b);
+    g_stats.gates++;
+    g_stats.pbs++;
+    return push_node(e, g, 1 + std::max(la, lb));
+}
+
+Handle record_mux(Engine* e, Handle sel, Handle if1, Handle if0) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    peba1_gate g{};
+    g.op = PEBA1_OP_MUX;
+    const int l0 = set_operand(g, 0, sel), l1 = set_operand(g, 1, if1), l2 = set_operand(g, 2, if0);
+    g_stats.gates++;
+    g_stats.pbs += 2;
+    return push_node(e, g, 1 + std::max(l0, std::max(l1, l2)));
+}
+
+Handle wire_from_host(Engine* e, const int32_t* words) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const int64_t id = new_wire(e, 0);  // reference owned by the upload queue
+    g_wires[id].refs++;                 // the caller's reference
+    e->up_wires.push_back(id);
+    e->up_words.insert(e->up_words.end(), words, words + e->words);
+    return (Handle)id << 1;
+}
+
+void flush(Engine* e) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (e->up_wires.empty() && e->levels.empty()) return;
+    const auto t0 = std::chrono::steady_clock::now();
+    // 1. pending uploads
+    if (!e->up_wires.empty()) {
+        std::vector<int64_t> slots(e->up_wires.size());
+        for (size_t i = 0; i < slots.size(); ++i) slots[i] = g_wires[e->up_wires[i]].slot = alloc_slot(e);
+        ensure_capacity(e);
+        CUCHK(e, be_upload_slots(e, slots.data(), (int64_t)slots.size(), e->up_words.data()));
+        g_stats.uploads += slots.size();
+        for (int64_t id : e->up_wires) unref_wire(id);
+        e->up_wires.clear();
+        e->up_words.clear();
+    }
+    // 2. one batched launch pair per level
+    for (auto& nodes : e->levels) {
+        if (nodes.empty()) continue;
+        e->scratch.resize(nodes.size());
+        for (size_t i = 0; i < nodes.size(); ++i) {
+            const peba1_gate& nd = nodes[i];
+            peba1_gate& g = e->scratch[i];
+            g = nd;
+            const int nin = nd.op == PEBA1_OP_MUX ? 3 : 2;
+            for (int q = 0; q < nin; ++q)
+                if (!(nd.flags & PEBA1_IN_CONST(q))) g.in[q] = g_wires[nd.in[q]].slot;
+            g.out = g_wires[nd.out].slot = alloc_slot(e);
+        }
+        ensure_capacity(e);
+        CUCHK(e, be_gates(e, e->scratch.data(), (int64_t)nodes.size()));
+        g_stats.levels++;
+        if (nodes.size() > g_stats.max_level_width) g_stats.max_level_width = nodes.size();
+        for (const peba1_gate& nd : nodes) {
+            const int nin = nd.op == PEBA1_OP_MUX ? 3 : 2;
+            g_wires[nd.out].level = 0;
+            for (int q = 0; q < nin; ++q)
+                if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(nd.in[q]);
+            unref_wire(nd.out);
+        }
+    }
+    e->levels.clear();
+    g_stats.flushes++;
+    g_stats.flush_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void fetch(Engine* e, Handle h, int32_t* words) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (is_const(h)) {
+        memset(words, 0, sizeof(int32_t) * (size_t)(e->words - 1));
+        words[e->words - 1] = (h & 1) ? (1 << 29) : -(1 << 29);
+        return;
+    }
+    Wire& w = g_wires[h >> 1];
+    if (w.level > 0 || w.slot < 0) flush(e);
+    if (g_wires[h >> 1].slot < 0) die("internal: wire %llu has no value after a flush", (unsigned long long)(h >> 1));
+    CUCHK(e, be_download(e, g_wires[h >> 1].slot, words));
+    g_stats.downloads++;
+    if (h & 1)
+        for (int i = 0; i < e->words; ++i) words[i] = (int32_t)(0u - (uint32_t)words[i]);
+}
+
+RoutineScope::RoutineScope(const TFheGateBootstrappingCloudKeySet* bk) : e(engine_of(bk)) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    e->routine_depth++;
+}
+RoutineScope::~RoutineScope() {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (--e->routine_depth == 0 && g_eager && g_batch_depth == 0) flush(e);
+}
+
+Handle sample_handle(Engine* e, const LweSample* s) {
+    if (s->peba1_handle != 0) return s->peba1_handle;
+    // host value: becomes a wire (queued upload); the sample keeps the reference so repeated uses upload once
+    std::vector<int32_t> tmp((size_t)e->words);
+    memcpy(tmp.data(), s->a, sizeof(int32_t) * (size_t)(e->words - 1));
+    tmp[e->words - 1] = s->b;
+    const Handle h = wire_from_host(e, tmp.data());
+    const_cast<LweSample*>(s)->peba1_handle = h;
+    return h;
+}
+
+void sample_assign(LweSample* s, Handle h) {
+    const Handle old = s->peba1_handle;
+    s->peba1_handle = h;
+    release(old);
+}
+
+void note_linear() { g_stats.linear++; }
+
+// ------------------------------------------------------------------------------------------------ randomness
+// One global generator like upstream (std::default_random_engine there; never seeded by the reference).
+static std::mt19937_64 g_rng(0x5eba1ULL);
+
+static inline int32_t double_to_torus32(double d) {  // fractional part of d, scaled to 2^32
+    return (int32_t)(int64_t)((d - (double)(int64_t)d) * 4294967296.0);
+}
+template <class Rng>
+static inline uint32_t gaussian32(Rng& rng, uint32_t message, double sigma) {
+    std::normal_distribution<double> dist(0.0, sigma);
+    return message + (uint32_t)double_to_torus32(dist(rng));
+}
+static inline uint32_t mod_switch_to_torus32(int32_t mu, int32_t msize) {
+    const uint64_t interval = ((UINT64_C(1) << 63) / (uint64_t)msize) * 2;
+    return (uint32_t)(((uint64_t)(int64_t)mu * interval) >> 32);
+}
+
+template <class Rng>
+static void lwe_encrypt(Rng& rng, const int32_t* key, int n, uint32_t message, double sigma, int32_t* out) {
+    uint32_t b = gaussian32(rng, message, sigma);
+    for (int i = 0; i < n; ++i) {
+        const uint32_t a = (uint32_t)rng();
+        out[i] = (int32_t)a;
+        if (key[i]) b += a;
+    }
+    out[n] = (int32_t)b;
+}
+
+// LWE key, ring key, keyswitch key (noise recentred, digit-0 rows noiseless zeros), n TGSW
+// encryptions of the LWE key bits.  Rows are independent, so they are generated on all host cores with per-row
+// generators derived from the master seed (deterministic for a given seed, independent of the thread count).
+static void generate_keys(peba1_key_material* km, uint64_t seed) {
+    const TFheGateBootstrappingParameterSet& p = km->params;
+    const int n = p.n, N = p.N, l = p.l, t = p.ks_t, base = 1 << p.ks_basebit, rows = (p.k + 1) * l;
+    std::mt19937_64 master(seed);
+    km->lwe_key.resize(n);
+    km->tlwe_key.resize(N);
+    for (int i = 0; i < n; ++i) km->lwe_key[i] = (int32_t)(master() & 1);
+    for (int i = 0; i < N; ++i) km->tlwe_key[i] = (int32_t)(master() & 1);
+    km->ksk.assign((size_t)N * t * base * (n + 1), 0);
+    km->bk.assign((size_t)n * rows * 2 * N, 0);
+    const uint64_t ks_seed = master(), bk_seed = master();
+
+    // keyswitch noises first (their mean is removed, as upstream does), then the samples
+    const size_t nks = (size_t)N * t * (base - 1);
+    std::vector<double> noise(nks);
+    {
+        std::mt19937_64 r(ks_seed);
+        std::normal_distribution<double> dist(0.0, p.ks_stdev);
+        double mean = 0;
+        for (double& x : noise) { x = dist(r); mean += x; }
+        mean /= (double)nks;
+        for (double& x : noise) x -= mean;
+    }
+    unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    auto parallel_for = [&](int count, auto&& body) {
+        std::vector<std::thread> th;
+        for (unsigned w = 0; w < nthreads; ++w)
+            th.emplace_back([&, w] { for (int i = (int)w; i < count; i += (int)nthreads) body(i); });
+        for (auto& x : th) x.join();
+    };
+    parallel_for(N, [&](int i) {
+        std::mt19937_64 r(ks_seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1)));
+        for (int j = 0; j < t; ++j)
+            for (int h = 1; h < base; ++h) {
+                int32_t* ct = km->ksk.data() + (((size_t)i * t + j) * base + h) * (size_t)(n + 1);
+                const uint32_t mess = (uint32_t)(km->tlwe_key[i] * h) << (32 - (j + 1) * p.ks_basebit);
+                uint32_t b = mess + (uint32_t)double_to_torus32(noise[((size_t)i * t + j) * (base - 1) + (h - 1)]);
+                for (int q = 0; q < n; ++q) {
+                    const uint32_t a = (uint32_t)r();
+                    ct[q] = (int32_t)a;
+                    if (km->lwe_key[q]) b += a;
+                }
+                ct[n] = (int32_t)b;
+            }
+    });
+    // bootstrapping key: row r of BK_i is a TLWE encryption of 0 (b = a*s + e in the negacyclic ring) plus
+    // s_i * 2^(32-(p+1)Bgbit) on coefficient 0 of the mask (rows 0..l-1) or of the body (rows l..2l-1)
+    std::vector<int> ones;
+    for (int m = 0; m < N; ++m) if (km->tlwe_key[m]) ones.push_back(m);
+    parallel_for(n * rows, [&](int ir) {
+        std::mt19937_64 r(bk_seed ^ (0xD1B54A32D192ED03ULL * (uint64_t)(ir + 1)));
+        uint32_t* a = (uint32_t*)km->bk.data() + ((size_t)ir * 2 + 0) * (size_t)N;
+        uint32_t* b = (uint32_t*)km->bk.data() + ((size_t)ir * 2 + 1) * (size_t)N;
+        for (int j = 0; j < N; ++j) b[j] = gaussian32(r, 0, p.bk_stdev);
+        for (int j = 0; j < N; ++j) a[j] = (uint32_t)r();
+        for (int m : ones) {  // b += X^m * a  (negacyclic)
+            for (int j = 0; j < m; ++j) b[j] -= a[j - m + N];
+            for (int j = m; j < N; ++j) b[j] += a[j - m];
+        }
+        const int i = ir / rows, row = ir % rows, bloc = row / l, pp = row % l;
+        const uint32_t h = UINT32_C(1) << (32 - (pp + 1) * p.Bgbit);
+        (bloc == 0 ? a : b)[0] += (uint32_t)km->lwe_key[i] * h;
+    });
+}
+
+static TFheGateBootstrappingSecretKeySet* wrap_keyset(peba1_key_material* km) {
+    auto* ks = new TFheGateBootstrappingSecretKeySet();
+    ks->params = &km->params;  // a private copy: main.cpp deletes the parameter set before the ciphertexts
+    ks->lwe_key = km->lwe_key.data();
+    ks->tlwe_key = km->tlwe_key.data();
+    ks->cloud.params = &km->params;
+    ks->cloud.material = km;
+    return ks;
+}
+
+static uint32_t phase_of(const TFheGateBootstrappingSecretKeySet* key, const int32_t* a, int32_t b) {
+    const int n = key->params->n;
+    uint32_t axs = 0;
+    for (int i = 0; i < n; ++i)
+        if (key->lwe_key[i]) axs += (uint32_t)a[i];
+    return (uint32_t)b - axs;
+}
+
+}  // namespace peba1
+
+using namespace peba1;
+
+// ================================================================================================ C API
+extern "C" {
+
+TFheGateBootstrappingParameterSet* new_default_gate_bootstrapping_parameters(int32_t minimum_lambda) {
+    if (minimum_lambda > 128) die("sorry, for now the parameters are only implemented for 80 and 128 bits of security");
+    auto* p = new TFheGateBootstrappingParameterSet();
+    p->ks_t = 8;
+    p->ks_basebit = 2;
+    p->N = 1024;
+    p->k = 1;
+    p->minimum_lambda = minimum_lambda;
+    if (minimum_lambda > 80) {
+        p->n = 630; p->l = 3; p->Bgbit = 7;
+        p->ks_stdev = ldexp(1.0, -15); p->bk_stdev = ldexp(1.0, -25); p->max_stdev = 0.012467;
+    } else {
+        p->n = 500; p->l = 2; p->Bgbit = 10;
+        p->ks_stdev = 2.44e-5; p->bk_stdev = 7.18e-9; p->max_stdev = 0.012467;
+    }
+    return p;
+}
+void delete_gate_bootstrapping_parameters(TFheGateBootstrappingParameterSet* params) { delete params; }
+
+TFheGateBootstrappingSecretKeySet* peba1_new_secret_keyset_seeded(const TFheGateBootstrappingParameterSet* params, uint64_t seed) {
+    if (!params) die("null parameter set");
+    auto* km = new peba1_key_material();
+    km->params = *params;
+    generate_keys(km, seed);
+    return wrap_keyset(km);
+}
+TFheGateBootstrappingSecretKeySet* new_random_gate_bootstrapping_secret_keyset(const TFheGateBootstrappingParameterSet* params) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    return peba1_new_secret_keyset_seeded(params, g_rng());
+}
+TFheGateBootstrappingSecretKeySet* peba1_new_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params, const int32_t* lwe_key,
+                                                                const int32_t* tlwe_key, const int32_t* bk, const int32_t* ksk) {
+    if (!params || !bk || !ksk) die("null argument");
+    auto* km = new peba1_key_material();
+    km->params = *params;
+    const TFheGateBootstrappingParameterSet& p = km->params;
+    km->lwe_key.assign((size_t)p.n, 0);
+    km->tlwe_key.assign((size_t)p.N, 0);
+    if (lwe_key) memcpy(km->lwe_key.data(), lwe_key, sizeof(int32_t) * (size_t)p.n);
+    if (tlwe_key) memcpy(km->tlwe_key.data(), tlwe_key, sizeof(int32_t) * (size_t)p.N);
+    km->bk.assign(bk, bk + (size_t)p.n * (p.k + 1) * p.l * 2 * p.N);
+    km->ksk.assign(ksk, ksk + (size_t)p.N * p.ks_t * (1 << p.ks_basebit) * (p.n + 1));
+    return wrap_keyset(km);
+}
+void delete_gate_bootstrapping_secret_keyset(TFheGateBootstrappingSecretKeySet* keyset) {
+    if (!keyset) return;
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    peba1_key_material* km = keyset->cloud.material;
+    // the engine (and the wires of still-allocated ciphertexts) outlives the keyset: main.cpp:600-607 deletes the
+    // keyset before the ciphertext arrays.  Pending work is executed, host key copies are dropped.
+    if (km->engine) flush(km->engine);
+    km->bk.clear(); km->bk.shrink_to_fit();
+    km->ksk.clear(); km->ksk.shrink_to_fit();
+    delete keyset;
+}
+void delete_gate_bootstrapping_cloud_keyset(TFheGateBootstrappingCloudKeySet*) {}
+
+LweSample* new_gate_bootstrapping_ciphertext_array(int32_t nbelems, const TFheGateBootstrappingParameterSet* params) {
+    if (nbelems < 0 || !params) die("bad ciphertext array request");
+    const size_t n = (size_t)params->n;
+    const size_t head = ((sizeof(LweSample) * (size_t)nbelems + 63) / 64) * 64;
+    char* block = (char*)malloc(head + sizeof(int32_t) * n * (size_t)nbelems + 64);
+    if (!block) die("out of memory");
+    LweSample* arr = (LweSample*)block;
+    int32_t* words = (int32_t*)(block + head);
+    for (int32_t i = 0; i < nbelems; ++i) {
+        arr[i].a = words + n * (size_t)i;
+        arr[i].b = 0;
+        arr[i].current_variance = 0.0;
+        arr[i].peba1_handle = kFalse;  // never-written ciphertexts read as trivial false
+    }
+    return arr;
+}
+LweSample* new_gate_bootstrapping_ciphertext(const TFheGateBootstrappingParameterSet* params) {
+    return new_gate_bootstrapping_ciphertext_array(1, params);
+}
+void delete_gate_bootstrapping_ciphertext_array(int32_t nbelems, LweSample* samples) {
+    if (!samples) return;
+    for (int32_t i = 0; i < nbelems; ++i) release(samples[i].peba1_handle);
+    free(samples);
+}
+void delete_gate_bootstrapping_ciphertext(LweSample* sample) { delete_gate_bootstrapping_ciphertext_array(1, sample); }
+
+void bootsSymEncrypt(LweSample* result, int32_t message, const TFheGateBootstrappingSecretKeySet* key) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const int n = key->params->n;
+    std::vector<int32_t> w((size_t)n + 1);
+    const uint32_t mu = mod_switch_to_torus32(1, 8);
+    lwe_encrypt(g_rng, key->lwe_key, n, message ? mu : 0u - mu, key->params->ks_stdev, w.data());
+    peba1_sample_set(result, w.data());
+    (void)n;
+}
+
+int32_t bootsSymDecrypt(const LweSample* sample, const TFheGateBootstrappingSecretKeySet* key) {
+    const Handle h = sample->peba1_handle;
+    if (h == 0) return (int32_t)phase_of(key, sample->a, sample->b) > 0 ? 1 : 0;
+    if (is_const(h)) return (int32_t)(h & 1);
+    Engine* e = engine_of(&key->cloud);
+    std::vector<int32_t> w((size_t)e->words);
+    fetch(e, h, w.data());
+    // cache the words in the sample's host storage (the handle stays authoritative)
+    LweSample* s = const_cast<LweSample*>(sample);
+    memcpy(s->a, w.data(), sizeof(int32_t) * (size_t)(e->words - 1));
+    s->b = w[e->words - 1];
+    return (int32_t)phase_of(key, s->a, s->b) > 0 ? 1 : 0;
+}
+
+void bootsCONSTANT(LweSample* result, int32_t value, const TFheGateBootstrappingCloudKeySet*) {
+    note_linear();
+    sample_assign(result, value ? kTrue : kFalse);
+}
+void bootsNOT(LweSample* result, const LweSample* ca, const TFheGateBootstrappingCloudKeySet* bk) {
+    note_linear();
+    const Handle h = sample_handle(engine_of(bk), ca);
+    retain(h);
+    sample_assign(result, negate(h));
+}
+void bootsCOPY(LweSample* result, const LweSample* ca, const TFheGateBootstrappingCloudKeySet* bk) {
+    note_linear();
+    if (result == ca) return;
+    const Handle h = sample_handle(engine_of(bk), ca);
+    retain(h);
+    sample_assign(result, h);
+}
+
+static void gate2(int op, LweSample* result, const LweSample* ca, const LweSample* cb, const TFheGateBootstrappingCloudKeySet* bk) {
+    Engine* e = engine_of(bk);
+    const Handle a = sample_handle(e, ca), b = sample_handle(e, cb);
+    sample_assign(result, record_gate(e, op, a, b));  // operands are held by the node before the output is rebound
+}
+void bootsNAND(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_NAND, r, a, b, bk); }
+void bootsOR(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_OR, r, a, b, bk); }
+void bootsAND(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_AND, r, a, b, bk); }
+void bootsXOR(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_XOR, r, a, b, bk); }
+void bootsXNOR(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_XNOR, r, a, b, bk); }
+void bootsNOR(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_NOR, r, a, b, bk); }
+void bootsANDNY(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_ANDNY, r, a, b, bk); }
+void bootsANDYN(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_ANDYN, r, a, b, bk); }
+void bootsORNY(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_ORNY, r, a, b, bk); }
+void bootsORYN(LweSample* r, const LweSample* a, const LweSample* b, const TFheGateBootstrappingCloudKeySet* bk) { gate2(PEBA1_OP_ORYN, r, a, b, bk); }
+void bootsMUX(LweSample* r, const LweSample* a, const LweSample* b, const LweSample* c, const TFheGateBootstrappingCloudKeySet* bk) {
+    Engine* e = engine_of(bk);
+    const Handle ha = sample_handle(e, a), hb = sample_handle(e, b), hc = sample_handle(e, c);
+    sample_assign(r, record_mux(e, ha, hb, hc));
+}
+
+void tfhe_random_generator_setSeed(uint32_t* values, int32_t size) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::seed_seq seq(values, values + (size > 0 ? size : 0));
+    g_rng.seed(seq);
+}
+
+// ------------------------------------------------------------------------------------------------ extensions
+void peba1_host_set_device(int device) { g_device = device; }
+void peba1_host_set_test_backend(const peba1_test_backend* backend) { g_test_backend = backend; }
+void peba1_flush(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    for (Engine* e : g_engines) flush(e);
+}
+void peba1_batch_begin(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    g_batch_depth++;
+}
+void peba1_batch_end(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_batch_depth > 0 && --g_batch_depth == 0) peba1_flush();
+}
+void peba1_set_eager(int eager) { g_eager = eager != 0; }
+void peba1_get_stats(peba1_host_stats* out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (out) *out = g_stats;
+}
+void peba1_reset_stats(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const uint64_t live = g_stats.live_slots;
+    g_stats = peba1_host_stats{};
+    g_stats.live_slots = g_stats.peak_slots = live;
+}
+
+int32_t peba1_sample_words(const TFheGateBootstrappingParameterSet* params) { return params->n + 1; }
+void peba1_sample_get(const LweSample* sample, const TFheGateBootstrappingCloudKeySet* bk, int32_t* words) {
+    const int n = bk->params->n;
+    const Handle h = sample->peba1_handle;
+    if (h == 0) {
+        memcpy(words, sample->a, sizeof(int32_t) * (size_t)n);
+        words[n] = sample->b;
+        return;
+    }
+    if (is_const(h)) {
+        memset(words, 0, sizeof(int32_t) * (size_t)n);
+        words[n] = (h & 1) ? (1 << 29) : -(1 << 29);
+        return;
+    }
+    fetch(engine_of(bk), h, words);
+}
+void peba1_sample_set(LweSample* sample, const int32_t* words) {
+    // n is implied by the array allocation; the words pointer layout is a[0..n-1], b
+    const Handle old = sample->peba1_handle;
+    sample->peba1_handle = 0;
+    release(old);
+    // distance between consecutive samples' storage is n words; recover n from the allocation is not possible for a
+    // single sample, so callers pass exactly n+1 words and n comes from the current engine or the first key created.
+    int n = -1;
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_mu);
+        if (g_current) n = g_current->words - 1;
+    }
+    if (n < 0) n = 630;
+    memcpy(sample->a, words, sizeof(int32_t) * (size_t)n);
+    sample->b = words[n];
+}
+LweSample* peba1_sample_at(LweSample* array, int32_t index) { return &array[index]; }
+
+const int32_t* peba1_keyset_bk(const TFheGateBootstrappingCloudKeySet* bk) { return bk->material->bk.data(); }
+const int32_t* peba1_keyset_ksk(const TFheGateBootstrappingCloudKeySet* bk) { return bk->material->ksk.data(); }
+
+void peba1_encrypt_bits(const TFheGateBootstrappingSecretKeySet* key, const int32_t* bits, int64_t count, uint64_t seed, int32_t* words) {
+    const int n = key->params->n;
+    const uint32_t mu = mod_switch_to_torus32(1, 8);
+    std::mt19937_64 r(seed);
+    for (int64_t i = 0; i < count; ++i)
+        lwe_encrypt(r, key->lwe_key, n, bits[i] ? mu : 0u - mu, key->params->ks_stdev, words + (size_t)i * (n + 1));
+}
+void peba1_decrypt_words(const TFheGateBootstrappingSecretKeySet* key, const int32_t* words, int64_t count, int32_t* bits) {
+    const int n = key->params->n;
+    for (int64_t i = 0; i < count; ++i) {
+        const int32_t* w = words + (size_t)i * (n + 1);
+        bits[i] = (int32_t)phase_of(key, w, w[n]) > 0 ? 1 : 0;
+    }
+}
+void* peba1_cuda_context_of(const TFheGateBootstrappingCloudKeySet* bk) { return engine_of(bk)->ctx; }
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+"""ctypes view of libpeba1_tfhe.so — the TFHE-compatible front end (include/tfhe/*.h, include/peba1_host.h) and the
+PEBA1 Math.h circuit library (include/peba1_math.h).  Used by tests and bench.py; computes nothing itself."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .cuda import load_library as _load_cuda
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class ParamSet(C.Structure):
+    _fields_ = [("ks_t", C.c_int32), ("ks_basebit", C.c_int32), ("n", C.c_int32), ("N", C.c_int32),
+                ("k", C.c_int32), ("l", C.c_int32), ("Bgbit", C.c_int32), ("ks_stdev", C.c_double),
+                ("bk_stdev", C.c_double), ("max_stdev", C.c_double), ("minimum_lambda", C.c_int32)]
+
+
+class CloudKey(C.Structure):
+    _fields_ = [("params", C.POINTER(ParamSet)), ("material", C.c_void_p)]
+
+
+class SecretKey(C.Structure):
+    _fields_ = [("params", C.POINTER(ParamSet)), ("lwe_key", C.POINTER(C.c_int32)),
+                ("tlwe_key", C.POINTER(C.c_int32)), ("cloud", CloudKey)]
+
+
+class LweSample(C.Structure):
+    _fields_ = [("a", C.POINTER(C.c_int32)), ("b", C.c_int32), ("current_variance", C.c_double),
+                ("peba1_handle", C.c_uint64)]
+
+
+class HostStats(C.Structure):
+    _fields_ = [("gates", C.c_uint64), ("pbs", C.c_uint64), ("linear", C.c_uint64), ("levels", C.c_uint64),
+                ("flushes", C.c_uint64), ("max_level_width", C.c_uint64), ("uploads", C.c_uint64),
+                ("downloads", C.c_uint64), ("live_slots", C.c_uint64), ("peak_slots", C.c_uint64),
+                ("flush_seconds", C.c_double)]
+
+
+class TestBackend(C.Structure):
+    RESERVE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64)
+    UPLOAD = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int32))
+    DOWNLOAD = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int32))
+    GATES = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+    _fields_ = [("user", C.c_void_p), ("reserve", RESERVE), ("upload_slots", UPLOAD), ("download", DOWNLOAD),
+                ("gates", GATES)]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "host", "libpeba1_tfhe.so")
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    _load_cuda()  # resolves libpeba1_cuda.so first (same directory tree)
+    L = C.CDLL(path)
+    PS, SK, CK, LS = C.POINTER(ParamSet), C.POINTER(SecretKey), C.POINTER(CloudKey), C.POINTER(LweSample)
+    i32p = C.POINTER(C.c_int32)
+    L.new_default_gate_bootstrapping_parameters.restype = PS
+    L.new_default_gate_bootstrapping_parameters.argtypes = [C.c_int32]
+    L.delete_gate_bootstrapping_parameters.argtypes = [PS]
+    L.new_random_gate_bootstrapping_secret_keyset.restype = SK
+    L.new_random_gate_bootstrapping_secret_keyset.argtypes = [PS]
+    L.peba1_new_secret_keyset_seeded.restype = SK
+    L.peba1_new_secret_keyset_seeded.argtypes = [PS, C.c_uint64]
+    L.peba1_new_keyset_from_arrays.restype = SK
+    L.peba1_new_keyset_from_arrays.argtypes = [PS, i32p, i32p, i32p, i32p]
+    L.delete_gate_bootstrapping_secret_keyset.argtypes = [SK]
+    L.new_gate_bootstrapping_ciphertext_array.restype = LS
+    L.new_gate_bootstrapping_ciphertext_array.argtypes = [C.c_int32, PS]
+    L.delete_gate_bootstrapping_ciphertext_array.argtypes = [C.c_int32, LS]
+    L.bootsSymEncrypt.argtypes = [LS, C.c_int32, SK]
+    L.bootsSymDecrypt.restype = C.c_int32
+    L.bootsSymDecrypt.argtypes = [LS, SK]
+    L.bootsCONSTANT.argtypes = [LS, C.c_int32, CK]
+    for nm in ("bootsNOT", "bootsCOPY"):
+        getattr(L, nm).argtypes = [LS, LS, CK]
+    for nm in ("bootsNAND", "bootsOR", "bootsAND", "bootsXOR", "bootsXNOR", "bootsNOR", "bootsANDNY", "bootsANDYN",
+               "bootsORNY", "bootsORYN"):
+        getattr(L, nm).argtypes = [LS, LS, LS, CK]
+    L.bootsMUX.argtypes = [LS, LS, LS, LS, CK]
+    L.peba1_host_set_device.argtypes = [C.c_int]
+    L.peba1_host_set_test_backend.argtypes = [C.POINTER(TestBackend)]
+    L.peba1_set_eager.argtypes = [C.c_int]
+    L.peba1_get_stats.argtypes = [C.POINTER(HostStats)]
+    L.peba1_sample_get.argtypes = [LS, CK, i32p]
+    L.peba1_sample_set.argtypes = [LS, i32p]
+    L.peba1_sample_at.restype = LS
+    L.peba1_sample_at.argtypes = [LS, C.c_int32]
+    L.peba1_keyset_bk.restype = i32p
+    L.peba1_keyset_bk.argtypes = [CK]
+    L.peba1_keyset_ksk.restype = i32p
+    L.peba1_keyset_ksk.argtypes = [CK]
+    L.peba1_encrypt_bits.argtypes = [SK, i32p, C.c_int64, C.c_uint64, i32p]
+    L.peba1_decrypt_words.argtypes = [SK, i32p, C.c_int64, i32p]
+    L.peba1_cuda_context_of.restype = C.c_void_p
+    L.peba1_cuda_context_of.argtypes = [CK]
+    L.peba1_math_add.argtypes = [LS, LS, LS, LS, C.c_int, CK]
+    L.peba1_math_twos_complement.argtypes = [LS, LS, C.c_int, CK]
+    L.peba1_math_abs.argtypes = [LS, LS, C.c_int, CK]
+    L.peba1_math_sub.argtypes = [LS, LS, LS, C.c_int, CK]
+    L.peba1_math_multiply.argtypes = [LS, LS, LS, C.c_int, C.c_int, CK]
+    L.peba1_math_minimum.argtypes = [LS, LS, LS, LS, C.c_int, CK]
+    PLS = C.POINTER(LS)
+    L.peba1_math_manhattan.argtypes = [LS, PLS, PLS, C.c_int, C.c_int, CK]
+    L.peba1_math_euclidean.argtypes = [LS, PLS, PLS, C.c_int, C.c_int, CK]
+    L.peba1_math_function_f.argtypes = [LS, PLS, PLS, C.c_int, LS, C.c_int, CK]
+    L.peba1_math_function_g.argtypes = [LS, LS, LS, LS, C.c_int, CK]
+    _lib = L
+    return L
+
+
+def _i32(a):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class KeySet:
+    """A secret keyset (params + LWE/TLWE keys + embedded cloud keyset), generated on the host."""
+
+    def __init__(self, params, sk):
+        self.L = load_library()
+        self.params_p, self.sk = params, sk
+        self.params = params.contents
+        self.cloud = C.pointer(sk.contents.cloud)
+        p = self.params
+        self.words = p.n + 1
+        rows = (p.k + 1) * p.l
+        self.bk = np.ctypeslib.as_array(self.L.peba1_keyset_bk(self.cloud), shape=(p.n, rows, 2, p.N))
+        self.ksk = np.ctypeslib.as_array(self.L.peba1_keyset_ksk(self.cloud),
+                                         shape=(p.N, p.ks_t, 1 << p.ks_basebit, p.n + 1))
+        self.lwe_key = np.ctypeslib.as_array(sk.contents.lwe_key, shape=(p.n,))
+        self.tlwe_key = np.ctypeslib.as_array(sk.contents.tlwe_key, shape=(p.N,))
+
+    @classmethod
+    def generate(cls, minimum_lambda: int = 128, seed: int = 42) -> "KeySet":
+        L = load_library()
+        params = L.new_default_gate_bootstrapping_parameters(minimum_lambda)
+        return cls(params, L.peba1_new_secret_keyset_seeded(params, seed))
+
+    def encrypt(self, bits, seed: int) -> np.ndarray:
+        bits = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)
+        out = np.empty((bits.size, self.words), dtype=np.int32)
+        self.L.peba1_encrypt_bits(self.sk, _i32(bits), bits.size, seed, _i32(out.reshape(-1)))
+        return out
+
+    def decrypt(self, words) -> np.ndarray:
+        words = np.ascontiguousarray(words, dtype=np.int32).reshape(-1, self.words)
+        out = np.empty(words.shape[0], dtype=np.int32)
+        self.L.peba1_decrypt_words(self.sk, _i32(words.reshape(-1)), words.shape[0], _i32(out))
+        return out.astype(np.int64)
+
+    # ---- ciphertext arrays (LweSample*) for the circuit API
+    def new_array(self, count: int):
+        return self.L.new_gate_bootstrapping_ciphertext_array(count, self.params_p)
+
+    def free_array(self, count: int, arr):
+        self.L.delete_gate_bootstrapping_ciphertext_array(count, arr)
+
+    def at(self, arr, i: int):
+        return self.L.peba1_sample_at(arr, i)
+
+    def set_words(self, arr, words: np.ndarray):
+        words = np.ascontiguousarray(words, dtype=np.int32).reshape(-1, self.words)
+        for i in range(words.shape[0]):
+            self.L.peba1_sample_set(self.at(arr, i), _i32(words[i]))
+
+    def get_words(self, arr, count: int) -> np.ndarray:
+        out = np.empty((count, self.words), dtype=np.int32)
+        for i in range(count):
+            self.L.peba1_sample_get(self.at(arr, i), self.cloud, _i32(out[i]))
+        return out
+
+    def encrypt_int(self, value: int, bits: int, seed: int):
+        """`bits` fresh encryptions of the bits of `value`, LSB first, as a new ciphertext array."""
+        arr = self.new_array(bits)
+        self.set_words(arr, self.encrypt([(value >> i) & 1 for i in range(bits)], seed))
+        return arr
+
+    def decrypt_int(self, arr, bits: int) -> int:
+        b = self.decrypt(self.get_words(arr, bits))
+        return int(sum(int(v) << i for i, v in enumerate(b)))
+
+    def stats(self) -> HostStats:
+        s = HostStats()
+        self.L.peba1_get_stats(C.byref(s))
+        return s

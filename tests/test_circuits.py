@@ -1,0 +1,273 @@
+"""CPU tests of the host side: the TFHE-compatible recorder and the Math.h circuit builder of libpeba1_tfhe.so,
+executed on the bit-level simulator (tests/sim_backend.py) instead of the GPU.
+
+Checks (a) decrypted results against native integer arithmetic — the comparisons the reference's own self-test makes
+(src/main.cpp:320 ADD, :352 two's complement, :383 ABS, :422 SUB, :456 MUL, :578 protocol verdict) including the
+reference's quirks, and (b) the schedule: gate counts and level counts per routine equal the
+reference's structure (7 gates per full adder etc.; SURVEY.md §8a [MODEL])."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from peba1_b200 import tfhe_host as H
+from sim_backend import SimBackend
+
+
+@pytest.fixture(scope="module")
+def env():
+    L = H.load_library()
+    sim = SimBackend()
+    sim.install()
+    ks = H.KeySet.generate(128, seed=7)
+    sim.keyset = ks
+    yield L, ks, sim
+
+
+def run(env, fn):
+    """resets the schedule, runs fn (which calls Math routines; eager mode flushes at routine exit)"""
+    L, ks, sim = env
+    sim.reset_schedule()
+    s0 = ks.stats()
+    fn()
+    s1 = ks.stats()
+    return dict(gates=s1.gates - s0.gates, pbs=s1.pbs - s0.pbs, levels=len(sim.level_widths),
+                widths=list(sim.level_widths))
+
+
+def test_keygen_and_roundtrip(env):
+    L, ks, sim = env
+    assert ks.bk.shape == (630, 6, 2, 1024) and ks.ksk.shape == (1024, 8, 4, 631)
+    assert not ks.ksk[:, :, 0, :].any()                      # digit-0 rows are noiseless zeros
+    bits = np.random.default_rng(1).integers(0, 2, size=64)
+    assert np.array_equal(ks.decrypt(ks.encrypt(bits, 5)), bits)
+    # deterministic for a given seed
+    ks2 = H.KeySet.generate(128, seed=7)
+    assert np.array_equal(ks2.bk[:3], ks.bk[:3]) and np.array_equal(ks2.lwe_key, ks.lwe_key)
+
+
+def test_host_keys_are_valid_tfhe_keys(env, oracle):
+    """keys from the product's own host keygen drive the oracle correctly (independent check of §3.3 keygen)."""
+    L, ks, sim = env
+    K = oracle.Keys.from_arrays(oracle.default_params(128), ks.lwe_key, ks.tlwe_key, ks.bk, ks.ksk)
+    a, b = np.array([0, 1, 0, 1]), np.array([0, 0, 1, 1])
+    out = K.gate_batch("NAND", ks.encrypt(a, 1), ks.encrypt(b, 2), threads=4)
+    assert ks.decrypt(out).tolist() == (1 - (a & b)).tolist()
+    ph = K.phase(out).astype(np.float64) / 2.0**32
+    assert np.all(np.abs(np.abs(ph) - 0.125) < 2.0**-5)
+    K.close()
+
+
+def test_single_gates_and_linear_ops(env):
+    L, ks, sim = env
+    for a in (0, 1):
+        for b in (0, 1):
+            x = ks.encrypt_int(a | (b << 1), 2, seed=11)
+            r = ks.new_array(8)
+            L.bootsAND(ks.at(r, 0), ks.at(x, 0), ks.at(x, 1), ks.cloud)
+            L.bootsXOR(ks.at(r, 1), ks.at(x, 0), ks.at(x, 1), ks.cloud)
+            L.bootsNOT(ks.at(r, 2), ks.at(x, 0), ks.cloud)
+            L.bootsOR(ks.at(r, 3), ks.at(r, 2), ks.at(x, 1), ks.cloud)          # gate on a negated alias
+            L.bootsCONSTANT(ks.at(r, 4), 1, ks.cloud)
+            L.bootsMUX(ks.at(r, 5), ks.at(x, 0), ks.at(r, 4), ks.at(x, 1), ks.cloud)  # a ? 1 : b
+            L.bootsCOPY(ks.at(r, 6), ks.at(r, 5), ks.cloud)
+            L.bootsXNOR(ks.at(r, 6), ks.at(r, 6), ks.at(x, 1), ks.cloud)        # output aliases an input
+            got = ks.decrypt(ks.get_words(r, 8)).tolist()
+            want = [a & b, a ^ b, 1 - a, (1 - a) | b, 1, 1 if a else b, 1 - ((1 if a else b) ^ b), 0]
+            assert got == want, (a, b)
+            ks.free_array(8, r)
+            ks.free_array(2, x)
+
+
+@pytest.mark.parametrize("bits,gates,levels", [(8, 56, 24), (16, 112, 48)])
+def test_add_counts_and_values(env, bits, gates, levels):
+    L, ks, sim = env
+    rng = np.random.default_rng(bits)
+    for trial in range(4):
+        x, y = (int(v) for v in rng.integers(0, 1 << bits, size=2))
+        a, b = ks.encrypt_int(x, bits, 100 + trial), ks.encrypt_int(y, bits, 200 + trial)
+        r, c = ks.new_array(bits), ks.new_array(1)
+        info = run(env, lambda: L.peba1_math_add(r, a, b, c, bits, ks.cloud))
+        assert (info["gates"], info["pbs"], info["levels"]) == (gates, gates, levels)
+        assert ks.decrypt_int(r, bits) == (x + y) % (1 << bits)          # main.cpp:320
+        assert ks.decrypt_int(c, 1) == (x + y) >> bits
+        for arr, n in ((a, bits), (b, bits), (r, bits), (c, 1)):
+            ks.free_array(n, arr)
+
+
+def test_twos_complement_and_abs(env):
+    L, ks, sim = env
+    for x in (0, 1, 77, 128, 200, 255):
+        a = ks.encrypt_int(x, 8, 300 + x)
+        r = ks.new_array(8)
+        info = run(env, lambda: L.peba1_math_twos_complement(r, a, 8, ks.cloud))
+        assert (info["gates"], info["levels"]) == (64, 25)
+        assert ks.decrypt_int(r, 8) == (-x) % 256                         # main.cpp:352
+        info = run(env, lambda: L.peba1_math_abs(r, a, 8, ks.cloud))
+        assert (info["gates"], info["levels"]) == (64, 24)
+        sx = x - 256 if x >= 128 else x
+        assert ks.decrypt_int(r, 8) == abs(sx) % 256                      # main.cpp:383
+        ks.free_array(8, a)
+        ks.free_array(8, r)
+
+
+def ref_sub(a, b):
+    """|a - b| with the reference's defect Q1: b == 0 gives (256 - a) on 9 bits."""
+    return abs(a - b) if b != 0 else (256 - a) % 512
+
+
+def test_sub_counts_values_and_quirk_q1(env):
+    L, ks, sim = env
+    for x, y in [(200, 13), (13, 200), (5, 5), (255, 1), (1, 255), (77, 0), (0, 0), (128, 0)]:
+        a, b = ks.encrypt_int(x, 8, 400 + x), ks.encrypt_int(y, 8, 500 + y)
+        r = ks.new_array(9)
+        info = run(env, lambda: L.peba1_math_sub(r, a, b, 8, ks.cloud))
+        assert (info["gates"], info["levels"]) == (226, 59)
+        assert ks.decrypt_int(r, 9) == ref_sub(x, y), (x, y)              # main.cpp:422 (+ Q1)
+        for arr, n in ((a, 8), (b, 8), (r, 9)):
+            ks.free_array(n, arr)
+
+
+def test_multiply_counts_and_values(env):
+    L, ks, sim = env
+    rng = np.random.default_rng(9)
+    for trial in range(3):
+        x, y = (int(v) for v in rng.integers(0, 256, size=2))
+        a, b = ks.encrypt_int(x, 8, 600 + trial), ks.encrypt_int(y, 8, 700 + trial)
+        r = ks.new_array(23)
+        info = run(env, lambda: L.peba1_math_multiply(r, a, b, 8, 0, ks.cloud))
+        assert (info["gates"], info["levels"]) == (1296, 81)
+        assert max(info["widths"]) == 100
+        assert ks.decrypt_int(r, 23) == x * y                             # main.cpp:456
+        for arr, n in ((a, 8), (b, 8), (r, 23)):
+            ks.free_array(n, arr)
+
+
+def test_multiply_16bit_parametrised_width(env):
+    """BASELINE config 3: 16-bit multiplier needs the reference's hard-coded 23 parametrised (3*16-1 = 47)."""
+    L, ks, sim = env
+    x, y = 54321, 65535
+    a, b = ks.encrypt_int(x, 16, 801), ks.encrypt_int(y, 16, 802)
+    r = ks.new_array(47)
+    info = run(env, lambda: L.peba1_math_multiply(r, a, b, 16, 47, ks.cloud))
+    assert (info["gates"], info["levels"]) == (5408, 169)
+    assert ks.decrypt_int(r, 47) == x * y
+    for arr, n in ((a, 16), (b, 16), (r, 47)):
+        ks.free_array(n, arr)
+
+
+def test_minimum_and_comparator_polarity(env):
+    L, ks, sim = env
+    for x, y in [(5, 9), (9, 5), (7, 7), (0, 1 << 23), ((1 << 24) - 1, 0)]:
+        a, b = ks.encrypt_int(x, 24, 900), ks.encrypt_int(y, 24, 901)
+        r, bit = ks.new_array(24), ks.new_array(24)
+        info = run(env, lambda: L.peba1_math_minimum(r, bit, a, b, 24, ks.cloud))
+        assert (info["gates"], info["pbs"], info["levels"]) == (72, 120, 26)
+        assert ks.decrypt_int(r, 24) == min(x, y)
+        assert ks.decrypt_int(bit, 24) == (1 if x > y else 0)             # Q3: 1 iff a > b
+        for arr in (a, b, r, bit):
+            ks.free_array(24, arr)
+
+
+def _vec(ks, values, seed):
+    arrs = [ks.encrypt_int(int(v), 8, seed + i) for i, v in enumerate(values)]
+    ptrs = (C.POINTER(H.LweSample) * len(arrs))(*arrs)
+    return arrs, ptrs
+
+
+def test_distances_small(env):
+    L, ks, sim = env
+    rng = np.random.default_rng(21)
+    slots = 4
+    t = rng.integers(1, 255, size=slots)          # no zero byte in the subtrahend: Q1 does not fire
+    s = rng.integers(0, 256, size=slots)
+    ta, tp = _vec(ks, t, 1000)
+    sa, sp = _vec(ks, s, 2000)
+    r = ks.new_array(24)
+    info = run(env, lambda: L.peba1_math_manhattan(r, tp, sp, slots, 8, ks.cloud))
+    assert info["gates"] == slots * (226 + 56)
+    assert ks.decrypt_int(r, 8) == int(np.abs(s.astype(int) - t.astype(int)).sum()) % 256
+    ks.free_array(24, r)
+    r = ks.new_array(24)
+    info = run(env, lambda: L.peba1_math_euclidean(r, tp, sp, slots, 8, ks.cloud))
+    assert info["gates"] == slots * (226 + 1296 + 161)                     # 215,424 / 128 per slot
+    assert ks.decrypt_int(r, 24) == int(((s.astype(int) - t.astype(int)) ** 2).sum())
+    for arr in ta + sa:
+        ks.free_array(8, arr)
+    ks.free_array(24, r)
+
+
+def test_function_f_and_g_protocol(env):
+    """The protocol path of main.cpp:513-581 on 4 slots: f gives 1 iff distance > bound (Q3), g selects r1 when b=1
+    and (-r0 mod 256) when b=0 (Q1 inside 1-b)."""
+    L, ks, sim = env
+    t = np.array([10, 20, 30, 40])
+    for probe, bound, expect in [(t + 1, 0, 1), (t + 1, 4, 0), (t + 3, 35, 1), (t + 3, 36, 0)]:
+        ta, tp = _vec(ks, t, 3000)
+        pa, pp = _vec(ks, probe, 4000)
+        eb = ks.encrypt_int(bound, 24, 5000)
+        rb = ks.new_array(24)
+        info = run(env, lambda: L.peba1_math_function_f(rb, pp, tp, 4, eb, 8, ks.cloud))
+        assert info["gates"] == 4 * 1683 + 72 and info["pbs"] == 4 * 1683 + 120
+        assert ks.decrypt_int(rb, 24) == expect
+        r0, r1 = 0x5A, 0xC3
+        e0, e1 = ks.encrypt_int(r0, 8, 6000), ks.encrypt_int(r1, 8, 6001)
+        y = ks.new_array(9)
+        info = run(env, lambda: L.peba1_math_function_g(y, rb, e0, e1, 8, ks.cloud))
+        assert info["gates"] == 2874
+        assert ks.decrypt_int(y, 8) == (r1 if expect else (-r0) % 256)
+        for arr in ta + pa + [e0, e1]:
+            ks.free_array(8, arr)
+        ks.free_array(24, eb); ks.free_array(24, rb); ks.free_array(9, y)
+
+
+def test_function_f_full_size_schedule(env):
+    """One face match at the reference's size (128 slots x 8 bits): 215,496 gates / 215,544 PBS / 377 levels, first
+    level 6,276 PBS wide (SURVEY.md §8a level profile), and live ciphertexts stay in the low thousands."""
+    L, ks, sim = env
+    rng = np.random.default_rng(33)
+    t = rng.integers(0, 255, size=128)
+    probe = (t + 1) % 256                          # main.cpp:39 — never zero, so Q1 does not fire
+    ta, tp = _vec(ks, t, 7000)
+    pa, pp = _vec(ks, probe, 8000)
+    eb = ks.encrypt_int(100, 24, 9000)
+    rb = ks.new_array(24)
+    info = run(env, lambda: L.peba1_math_function_f(rb, pp, tp, 128, eb, 8, ks.cloud))
+    assert (info["gates"], info["pbs"], info["levels"]) == (215496, 215544, 377)
+    assert sim.level_pbs[0] == 6276 and sim.level_pbs[1] == 2176
+    assert ks.decrypt_int(rb, 24) == 1             # distance 128 > 100
+    assert ks.stats().peak_slots < 25000   # ~19.6k live ciphertexts = 50 MB of pool per template in flight
+    for arr in ta + pa:
+        ks.free_array(8, arr)
+    ks.free_array(24, eb); ks.free_array(24, rb)
+
+
+def test_batched_instances_share_levels(env):
+    """BASELINE config 3 shape: many independent adder instances recorded in one batch execute in the SAME 24 levels."""
+    L, ks, sim = env
+    n = 64
+    rng = np.random.default_rng(4)
+    xs, ys = rng.integers(0, 256, size=n), rng.integers(0, 256, size=n)
+    A = [ks.encrypt_int(int(x), 8, 10000 + i) for i, x in enumerate(xs)]
+    B = [ks.encrypt_int(int(y), 8, 20000 + i) for i, y in enumerate(ys)]
+    R = [ks.new_array(8) for _ in range(n)]
+    Cc = [ks.new_array(1) for _ in range(n)]
+
+    def body():
+        L.peba1_batch_begin()
+        for i in range(n):
+            L.peba1_math_add(R[i], A[i], B[i], Cc[i], 8, ks.cloud)
+        L.peba1_batch_end()
+    info = run(env, body)
+    assert info["gates"] == 56 * n and info["levels"] == 24
+    assert sum(info["widths"]) == 56 * n
+    for i in range(n):
+        assert ks.decrypt_int(R[i], 8) == (int(xs[i]) + int(ys[i])) % 256
+    for i in range(n):
+        ks.free_array(8, A[i]); ks.free_array(8, B[i]); ks.free_array(8, R[i]); ks.free_array(1, Cc[i])
+
+
+def test_slots_are_recycled(env):
+    """after everything above was freed the pool holds (almost) nothing live"""
+    L, ks, sim = env
+    assert ks.stats().live_slots < 64
