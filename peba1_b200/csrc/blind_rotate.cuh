@@ -72,35 +72,36 @@ PEBA1_HD void blind_rotate_team(Env& env, TeamSmem& sm, const TeamTwiddles& tw, 
 #pragma unroll
         for (int q = 0; q < 8; ++q) { sum0[q] = make_double2(0.0, 0.0); sum1[q] = make_double2(0.0, 0.0); }
 
-#pragma unroll
-        for (int poly = 0; poly < 2; ++poly) {
-            uint32_t tv[16];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
-                tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
-            }
-#pragma unroll
-            for (int p = 0; p < L; ++p) {
-                constexpr int dummy = 0; (void)dummy;
-                const int shift = 32 - (p + 1) * BGBIT;
-                double2 x[8];
+        // Rows are a real loop (not unrolled): six copies of the transform overflow the instruction cache
+        // (ncu r1a: icc hit rate 76%, "no instruction" stalls).  The digit shift is a run-time value instead.
+        uint32_t tv[16];
+#pragma unroll 1
+        for (int r = 0; r < ROWS; ++r) {
+            const int poly = r >= L ? 1 : 0;
+            const int p = r - poly * L;
+            if (p == 0) {
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
-                    const int32_t dr = (int32_t)((tv[a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
-                    const int32_t di = (int32_t)((tv[8 + a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
-                    x[a] = make_double2(i2d(dr), i2d(di));
+                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
+                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
                 }
-                const int r = poly * L + p;
-                team_fft_forward(env, x, tw, sm, r & 1);
-                const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
+            }
+            const int shift = 32 - (p + 1) * BGBIT;
+            double2 x[8];
 #pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) {
-                    const double2 b0 = env.ldg2(bk + (size_t)(2 * k2 + 0) * 64);
-                    const double2 b1 = env.ldg2(bk + (size_t)(2 * k2 + 1) * 64);
-                    cfma(sum0[k2], x[k2], b0);
-                    cfma(sum1[k2], x[k2], b1);
-                }
+            for (int a = 0; a < 8; ++a) {
+                const int32_t dr = (int32_t)((tv[a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
+                const int32_t di = (int32_t)((tv[8 + a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
+                x[a] = make_double2(i2d(dr), i2d(di));
+            }
+            team_fft_forward(env, x, tw, sm, r & 1);
+            const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {
+                const double2 b0 = env.ldg2(bk + (size_t)(2 * k2 + 0) * 64);
+                const double2 b1 = env.ldg2(bk + (size_t)(2 * k2 + 1) * 64);
+                cfma(sum0[k2], x[k2], b0);
+                cfma(sum1[k2], x[k2], b1);
             }
         }
         // inverse transforms and accumulator update (round to nearest, wrap mod 2^32)

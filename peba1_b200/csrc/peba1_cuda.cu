@@ -59,11 +59,15 @@ struct DevEnv {
 
 __constant__ TwiddleTables c_tables;
 
+// The per-thread twiddles are read ONCE into registers.  They must not be rematerialised from constant memory
+// inside the iteration loop: a thread-indexed LDC serialises over the warp (ncu r1b: 60% of all stall samples sat on
+// the first DMUL after such loads), so every value is laundered through an empty asm that hides its origin.
 __device__ __forceinline__ void load_twiddles_dev(int tid, TeamTwiddles& tw) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         tw.tw1[j] = c_tables.tw1[tid][j];
         tw.tw2[j] = c_tables.tw2[tid & 7][j];
+        asm volatile("" : "+d"(tw.tw1[j].x), "+d"(tw.tw1[j].y), "+d"(tw.tw2[j].x), "+d"(tw.tw2[j].y));
     }
 }
 
@@ -259,7 +263,7 @@ struct peba1_cuda_ctx {
     int32_t* h_stage = nullptr;  // pinned
     size_t h_stage_cap = 0;
     // options
-    int teams_per_cta = 4;
+    int teams_per_cta = 6;
     int64_t max_pbs_per_launch = 1 << 18;
     // stats
     bool timing = false;
@@ -334,8 +338,9 @@ int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const Pbs
         case 1: rc = launch_pbs_t<1>(c, pool, stride, jobs, count, u); break;
         case 2: rc = launch_pbs_t<2>(c, pool, stride, jobs, count, u); break;
         case 3: rc = launch_pbs_t<3>(c, pool, stride, jobs, count, u); break;
-        case 6: rc = launch_pbs_t<6>(c, pool, stride, jobs, count, u); break;
-        default: rc = launch_pbs_t<4>(c, pool, stride, jobs, count, u); break;
+        case 5: rc = launch_pbs_t<5>(c, pool, stride, jobs, count, u); break;
+        case 4: rc = launch_pbs_t<4>(c, pool, stride, jobs, count, u); break;
+        default: rc = launch_pbs_t<6>(c, pool, stride, jobs, count, u); break;
     }
     if (rc) return rc;
     if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
@@ -853,8 +858,8 @@ int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* c, double* tflops) {
 int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return fail(PEBA1_EINVAL, "null argument");
     if (!strcmp(name, "teams_per_cta")) {
-        if (value == 0) value = 4;
-        if (value != 1 && value != 2 && value != 3 && value != 4 && value != 6) return fail(PEBA1_EINVAL, "teams_per_cta must be 1, 2, 3, 4 or 6");
+        if (value == 0) value = 6;
+        if (value < 1 || value > 6) return fail(PEBA1_EINVAL, "teams_per_cta must be 1..6");
         c->teams_per_cta = (int)value;
         return 0;
     }

@@ -14,7 +14,7 @@ eng.reserve(3*n); eng.upload(0, cts)
 eng.enable_timing(True)
 from peba1_b200.cuda import make_gates
 g = make_gates("NAND", np.arange(n), n+np.arange(n), 2*n+np.arange(n))
-for teams in (4, 3, 2, 6, 1):
+for teams in (4, 5, 6):
     eng.set_option("teams_per_cta", teams)
     for rep in range(2):
         eng.gates(g)
