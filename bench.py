@@ -37,10 +37,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="gates per GPU per step")
     ap.add_argument("--op", default="NAND", choices=["NAND", "XOR", "MUX"])
-    ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU baseline sample (0: cores*24)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU baseline sample (0: cores*512, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-face-match", action="store_true")
-    ap.add_argument("--face-templates", type=int, default=0, help="templates in the face-match leg (0: skip unless set)")
+    ap.add_argument("--face-templates", type=int, default=2, help="templates per GPU in the face-match leg (0: skip)")
     return ap.parse_args()
 
 
@@ -117,7 +117,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    gates = args.cpu_sample or cores * 24
+    gates = args.cpu_sample or cores * 96
     rate, dt = cpu_reference_rate(args.op, gates, cores, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "bootstrapped gates/s (PBS/s)", "value": rate, "unit": "PBS/s",
@@ -140,20 +140,93 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def make_keys(p):
-    """Host key generation through the product's own TFHE-compatible shim when built; else random key words
-    (timing only — the arithmetic is data-independent)."""
-    import numpy as np
-    try:
-        from peba1_b200 import tfhe_host
-        ks = tfhe_host.KeySet.generate(128, seed=KEY_SEED)
-        return ks, ks.bk, ks.ksk, "host keygen (libpeba1_tfhe), seed 42"
-    except Exception:
-        rng = np.random.default_rng(KEY_SEED)
-        bk = rng.integers(-2**31, 2**31, size=p.n * 2 * p.l * 2 * p.N, dtype=np.int64).astype(np.int32)
-        ksk = rng.integers(-2**31, 2**31, size=p.N * p.ks_t * (1 << p.ks_basebit) * (p.n + 1),
-                           dtype=np.int64).astype(np.int32)
-        return None, bk, ksk, "uniform random key words (timing only)"
+def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np):
+    """Encrypted face matches/s (BASELINE metric, second half): Function_f = 128-dim 8-bit squared distance + 24-bit
+    threshold compare, one probe against `T` templates per GPU, all templates of a rank recorded into ONE batch so each
+    of the 377 circuit levels is one launch pair.  Rank 0 plays the client (encrypts, decrypts); template ciphertexts
+    are scattered and the encrypted match bits gathered with NCCL."""
+    import ctypes as C
+    from peba1_b200 import tfhe_host as H
+    L = H.load_library()
+    T = args.face_templates
+    slots, bits, words = 128, 8, ks.words
+    dev = f"cuda:{local}"
+    rng = np.random.default_rng(2024)
+    probe = rng.integers(1, 256, size=slots)                     # no zero byte: reference quirk Q1 stays silent
+    gallery = rng.integers(0, 256, size=(world * T, slots))
+    planted = rng.random(world * T) < 0.25                        # a quarter of the gallery are near-copies
+    gallery[planted] = np.clip(probe + rng.integers(-2, 3, size=(int(planted.sum()), slots)), 0, 255)
+    dist2 = ((gallery.astype(np.int64) - probe) ** 2).sum(axis=1)
+    bound = 128 * 4
+    expect = (dist2 > bound).astype(np.int64)                     # comparator polarity Q3: 1 iff distance > bound
+
+    def bits_of(vec, nb):
+        return np.array([[(int(v) >> j) & 1 for j in range(nb)] for v in vec]).reshape(-1)
+
+    probe_t = torch.empty((slots * bits, words), dtype=torch.int32, device=dev)
+    bound_t = torch.empty((24, words), dtype=torch.int32, device=dev)
+    mine_t = torch.empty((T, slots * bits, words), dtype=torch.int32, device=dev)
+    if rank == 0:
+        probe_t.copy_(torch.from_numpy(ks.encrypt(bits_of(probe, bits), 501)))
+        bound_t.copy_(torch.from_numpy(ks.encrypt(bits_of([bound], 24), 502)))
+        allg = ks.encrypt(bits_of(gallery.reshape(-1), bits), 503).reshape(world, T, slots * bits, words)
+        chunks = [torch.from_numpy(np.ascontiguousarray(allg[r])).to(dev) for r in range(world)]
+    if dist is not None:
+        dist.broadcast(probe_t, 0)
+        dist.broadcast(bound_t, 0)
+        dist.scatter(mine_t, chunks if rank == 0 else None, src=0)
+    else:
+        mine_t.copy_(chunks[0])
+    probe_w, bound_w, mine_w = probe_t.cpu().numpy(), bound_t.cpu().numpy(), mine_t.cpu().numpy()
+
+    LSP = C.POINTER(H.LweSample)
+    def vec(wordsarr):
+        arrs = []
+        for i in range(slots):
+            a = ks.new_array(bits)
+            ks.set_words(a, wordsarr[i * bits:(i + 1) * bits])
+            arrs.append(a)
+        return arrs, (LSP * slots)(*arrs)
+    pa, pp = vec(probe_w)
+    eb = ks.new_array(24)
+    ks.set_words(eb, bound_w)
+    tv = [vec(mine_w[t]) for t in range(T)]
+    rb = [ks.new_array(24) for _ in range(T)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    s0 = ks.stats()
+    c0 = eng.stats().launches
+    barrier()
+    t0 = time.perf_counter()
+    L.peba1_batch_begin()
+    for t in range(T):
+        L.peba1_math_function_f(rb[t], pp, tv[t][1], slots, eb, bits, ks.cloud)
+    L.peba1_batch_end()                                           # 377 levels, each one blind-rotation + keyswitch launch
+    out = np.stack([ks.get_words(rb[t], 1)[0] for t in range(T)])
+    out_t = torch.from_numpy(out).to(dev)
+    gathered = [torch.empty_like(out_t) for _ in range(world)] if dist is not None else [out_t]
+    if dist is not None:
+        dist.all_gather(gathered, out_t)                          # encrypted match bits over NVLink
+    barrier()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    s1 = ks.stats()
+    res = {"value": world * T / dt, "unit": "face matches/s", "templates": world * T, "templates_per_gpu": T,
+           "seconds": dt, "pbs": int(s1.pbs - s0.pbs) * world, "pbs_per_s": (s1.pbs - s0.pbs) * world / dt,
+           "levels": int(s1.levels - s0.levels), "gpu_launches": int(eng.stats().launches - c0),
+           "workload": f"Function_f (128-dim 8-bit squared distance + 24-bit threshold), 1 probe vs {world * T} templates, "
+                       "215,544 bootstraps per match", "timing": "wall clock incl. host recording, max over ranks"}
+    if rank == 0:
+        got = ks.decrypt(torch.stack(gathered).cpu().numpy().reshape(-1, words))
+        res["verified"] = bool(np.array_equal(got, expect))
+        res["matches_found"] = int((got == 0).sum())
+    return res
 
 
 def main():
@@ -164,6 +237,7 @@ def main():
     import numpy as np
     import torch
     import peba1_b200 as P
+    from peba1_b200 import tfhe_host as H
     from peba1_b200.cuda import make_gates
 
     rank = int(os.environ.get("RANK", "0"))
@@ -180,18 +254,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- keys: rank 0 is the key holder: host keygen (libpeba1_tfhe), integer keys uploaded once and transformed on
+    # its GPU; the other ranks create key-less contexts and receive the DEVICE-format keys by NCCL broadcast over NVLink.
+    H.load_library().peba1_host_set_device(local)
     p = P.default_params(128)
-    eng = P.Engine(p, device=local)
+    ks = H.KeySet.generate(128, seed=KEY_SEED) if rank == 0 else H.KeySet.placeholder(128)
+    eng = P.Engine.from_handle(ks.cuda_context(), p, device=local)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
-
-    # ---- keys: rank 0 generates on the host and transforms on its GPU; the others receive the device-format keys
-    # over NCCL/NVLink (north_star: "keys are replicated by NCCL broadcast").
-    keyset, key_note = None, ""
-    if rank == 0:
-        keyset, bk, ksk, key_note = make_keys(p)
-        eng.load_keys(bk, ksk)
-        del bk, ksk
     if dist is not None:
         (pa, na), (pb, nb) = eng.key_device_buffers()
         ta = torch.as_tensor(_DevPtr(pa, na), device=f"cuda:{local}")
@@ -200,23 +270,26 @@ def main():
         dist.broadcast(tb, 0)
         torch.cuda.synchronize()
         eng.keys_mark_loaded()
+    key_note = "host keygen (libpeba1_tfhe) seed 42 on rank 0" + ("; device-format keys NCCL-broadcast" if world > 1 else "")
 
-    # ---- inputs: random ciphertexts (real encryptions when the host keygen is available), resident in the pool
+    # ---- inputs resident in the pool: rank 0 uses real encryptions of random bits (and verifies the decrypted outputs
+    # of the timed batch); the other ranks use random words (the arithmetic is data-independent)
     B = args.batch
     nin = 3 if args.op == "MUX" else 2
     words = p.n + 1
     rng = np.random.default_rng(1000 + rank)
     bits = rng.integers(0, 2, size=(nin, B))
-    if keyset is not None and world == 1:
-        host_in = keyset.encrypt(bits.reshape(-1), seed=77 + rank).reshape(nin, B, words)
+    if rank == 0:
+        host_in = ks.encrypt(bits.reshape(-1), seed=77).reshape(nin, B, words)
     else:
         host_in = rng.integers(-2**31, 2**31, size=(nin, B, words), dtype=np.int64).astype(np.int32)
     pinned_in = torch.empty((nin, B, words), dtype=torch.int32).pin_memory()
     pinned_in.numpy()[...] = host_in
     pinned_out = torch.empty((B, words), dtype=torch.int32).pin_memory()
-    eng.reserve((nin + 1) * B)
-    eng.upload(0, host_in.reshape(-1, words))
-    idx = np.arange(B)
+    base = 1 << 20                                 # bench slots sit above anything the recorder allocates
+    eng.reserve(base + (nin + 1) * B)
+    eng.upload(base, host_in.reshape(-1, words))
+    idx = base + np.arange(B)
     gates = make_gates(args.op, idx, B + idx, nin * B + idx, in2=(2 * B + idx) if args.op == "MUX" else None)
     pbs_per_step = B * (2 if args.op == "MUX" else 1)
 
@@ -224,7 +297,8 @@ def main():
     eng.enable_timing(True)
 
     # ---- device-resident throughput
-    for _ in range(max(args.warmup, 3) if args.warmup >= 0 else 3):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         eng.gates(gates)
     eng.reset_stats()
     sampler = ClockSampler(local)
@@ -243,11 +317,15 @@ def main():
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = float(t.item()) / args.steps
     value = world * pbs_per_step / (ms_step * 1e-3)
     br_ms = st.sum_blind_rotate_ms / args.steps
     ks_ms = st.sum_keyswitch_ms / args.steps
+    verified = None
+    if rank == 0:
+        a, b = bits[0], bits[1]
+        want = {"NAND": 1 - (a & b), "XOR": a ^ b, "MUX": np.where(a == 1, b, bits[2] if nin == 3 else 0)}[args.op]
+        verified = bool(np.array_equal(ks.decrypt(eng.download(base + nin * B, B)), want))
 
     # ---- end to end through the host-buffer C-ABI call (upload + run + download inside the timed region)
     eng.enable_timing(False)
@@ -265,28 +343,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
     e2e_value = world * pbs_per_step / (e2e_ms * 1e-3)
+    if rank == 0:
+        verified = verified and bool(np.array_equal(ks.decrypt(pinned_out.numpy()), want))
 
-    # ---- correctness of what was timed (decrypted bits), when real keys are in use
-    verified = None
-    if keyset is not None and world == 1:
-        got = keyset.decrypt(pinned_out.numpy())
-        a, b = bits[0], bits[1]
-        want = {"NAND": 1 - (a & b), "XOR": a ^ b, "MUX": np.where(a == 1, b, bits[2] if nin == 3 else 0)}[args.op]
-        verified = bool(np.array_equal(got, want))
-        if not verified:
-            print("ERROR: decrypted outputs of the timed batch are wrong", file=sys.stderr)
-            sys.exit(1)
+    # ---- encrypted face matches/s on a bounded number of templates per GPU
+    face = None
+    if not args.no_face_match and args.face_templates > 0:
+        face = face_match_leg(args, ks, eng, dist, rank, world, local, torch, np)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    if verified is False or (face and face.get("verified") is False):
+        print("ERROR: decrypted outputs of the timed work are wrong", file=sys.stderr)
+        sys.exit(1)
 
     # ---- CPU baseline beside it (bounded sample), rank 0, N=1 only
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        g = args.cpu_sample or cores * 24
+        g = args.cpu_sample or cores * 512
         rate, dt = cpu_reference_rate(args.op, g, cores)
         cpu = {"value": rate, "unit": "PBS/s", "cores": cores, "kind": "port",
                "sample": f"{g} boots{args.op} gates, one gate per thread on {cores} threads, oracle FP64-FFT form, {dt:.1f} s"}
@@ -301,7 +378,7 @@ def main():
     ks_bytes = KSK_BYTES + B * (4100 + 2524)
     line = {
         "metric": "bootstrapped gates/s (PBS/s)", "value": value, "unit": "PBS/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"gate-bootstrap microbench (BASELINE configs[1]): batch of {B} boots{args.op} per GPU on "
                                "random ciphertexts, n=630 N=1024 k=1 l=3 Bgbit=7, keyswitch t=8 base 4",
@@ -323,6 +400,7 @@ def main():
                                "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
                                "note": "algorithmic bytes = 62.0 MB key + batch x (4100 in + 2524 out); peak = "
                                        "MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
+        "face_match": face,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

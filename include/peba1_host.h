@@ -64,6 +64,10 @@ TFheGateBootstrappingSecretKeySet* peba1_new_secret_keyset_seeded(const TFheGate
 TFheGateBootstrappingSecretKeySet* peba1_new_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params,
                                                                 const int32_t* lwe_key, const int32_t* tlwe_key,
                                                                 const int32_t* bk, const int32_t* ksk);
+/* Multi-GPU replicas: a keyset with no key material.  Its GPU context is created without keys; the caller fills the
+   device key buffers (peba1_cuda_key_device_buffers on peba1_cuda_context_of) with an NCCL broadcast from the rank that
+   holds the real keys, then calls peba1_cuda_keys_mark_loaded.  It cannot encrypt or decrypt. */
+TFheGateBootstrappingSecretKeySet* peba1_new_placeholder_keyset(const TFheGateBootstrappingParameterSet* params);
 const int32_t* peba1_keyset_bk(const TFheGateBootstrappingCloudKeySet* bk);   /* [n][2l][2][N] */
 const int32_t* peba1_keyset_ksk(const TFheGateBootstrappingCloudKeySet* bk);  /* [N][t][2^basebit][n+1] */
 /* Batch encryption with an explicit seed: bits[count] -> words[count][n+1]. */

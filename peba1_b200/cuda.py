@@ -134,11 +134,26 @@ class Engine:
         self.device = device
         self.words = self.params.n + 1
 
+    @classmethod
+    def from_handle(cls, handle: int, params: Params, device: int = 0) -> "Engine":
+        """Wraps a context owned by someone else (e.g. the one behind a libpeba1_tfhe keyset); close() is a no-op."""
+        self = cls.__new__(cls)
+        self.L = load_library()
+        self.params = params
+        self.h = C.c_void_p(handle)
+        self.device = device
+        self.words = params.n + 1
+        self._borrowed = True
+        return self
+
     def _chk(self, rc: int):
         if rc != 0:
             raise PEBA1Error(rc, (self.L.peba1_cuda_last_error() or b"").decode())
 
     def close(self):
+        if getattr(self, "_borrowed", False):
+            self.h = None
+            return
         if getattr(self, "h", None):
             self.L.peba1_cuda_destroy(self.h)
             self.h = None

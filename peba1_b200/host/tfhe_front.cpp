@@ -112,8 +112,10 @@ Engine* engine_of(const TFheGateBootstrappingCloudKeySet* bk) {
             peba1_cuda_params p{km->params.n, km->params.N, km->params.k, km->params.l, km->params.Bgbit,
                                 km->params.ks_t, km->params.ks_basebit};
             CUCHK(e, peba1_cuda_create(pick_device(), &p, &e->ctx));
-            CUCHK(e, peba1_cuda_load_bootstrap_key(e->ctx, km->bk.data()));
-            CUCHK(e, peba1_cuda_load_keyswitch_key(e->ctx, km->ksk.data()));
+            if (!km->bk.empty()) {  // a placeholder keyset receives its device-format keys by NCCL broadcast instead
+                CUCHK(e, peba1_cuda_load_bootstrap_key(e->ctx, km->bk.data()));
+                CUCHK(e, peba1_cuda_load_keyswitch_key(e->ctx, km->ksk.data()));
+            }
         }
         g_engines.push_back(e);
         km->engine = e;
@@ -504,6 +506,14 @@ TFheGateBootstrappingSecretKeySet* peba1_new_keyset_from_arrays(const TFheGateBo
     km->ksk.assign(ksk, ksk + (size_t)p.N * p.ks_t * (1 << p.ks_basebit) * (p.n + 1));
     return wrap_keyset(km);
 }
+TFheGateBootstrappingSecretKeySet* peba1_new_placeholder_keyset(const TFheGateBootstrappingParameterSet* params) {
+    if (!params) die("null parameter set");
+    auto* km = new peba1_key_material();
+    km->params = *params;
+    km->lwe_key.assign((size_t)params->n, 0);
+    km->tlwe_key.assign((size_t)params->N, 0);
+    return wrap_keyset(km);
+}
 void delete_gate_bootstrapping_secret_keyset(TFheGateBootstrappingSecretKeySet* keyset) {
     if (!keyset) return;
     std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -673,8 +683,8 @@ void peba1_sample_set(LweSample* sample, const int32_t* words) {
 }
 LweSample* peba1_sample_at(LweSample* array, int32_t index) { return &array[index]; }
 
-const int32_t* peba1_keyset_bk(const TFheGateBootstrappingCloudKeySet* bk) { return bk->material->bk.data(); }
-const int32_t* peba1_keyset_ksk(const TFheGateBootstrappingCloudKeySet* bk) { return bk->material->ksk.data(); }
+const int32_t* peba1_keyset_bk(const TFheGateBootstrappingCloudKeySet* bk) { return bk->material->bk.empty() ? nullptr : bk->material->bk.data(); }
+const int32_t* peba1_keyset_ksk(const TFheGateBootstrappingCloudKeySet* bk) { return bk->material->ksk.empty() ? nullptr : bk->material->ksk.data(); }
 
 void peba1_encrypt_bits(const TFheGateBootstrappingSecretKeySet* key, const int32_t* bits, int64_t count, uint64_t seed, int32_t* words) {
     const int n = key->params->n;

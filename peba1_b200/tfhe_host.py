@@ -73,6 +73,8 @@ def load_library():
     L.peba1_new_secret_keyset_seeded.argtypes = [PS, C.c_uint64]
     L.peba1_new_keyset_from_arrays.restype = SK
     L.peba1_new_keyset_from_arrays.argtypes = [PS, i32p, i32p, i32p, i32p]
+    L.peba1_new_placeholder_keyset.restype = SK
+    L.peba1_new_placeholder_keyset.argtypes = [PS]
     L.delete_gate_bootstrapping_secret_keyset.argtypes = [SK]
     L.new_gate_bootstrapping_ciphertext_array.restype = LS
     L.new_gate_bootstrapping_ciphertext_array.argtypes = [C.c_int32, PS]
@@ -134,9 +136,9 @@ class KeySet:
         p = self.params
         self.words = p.n + 1
         rows = (p.k + 1) * p.l
-        self.bk = np.ctypeslib.as_array(self.L.peba1_keyset_bk(self.cloud), shape=(p.n, rows, 2, p.N))
-        self.ksk = np.ctypeslib.as_array(self.L.peba1_keyset_ksk(self.cloud),
-                                         shape=(p.N, p.ks_t, 1 << p.ks_basebit, p.n + 1))
+        bkp, kskp = self.L.peba1_keyset_bk(self.cloud), self.L.peba1_keyset_ksk(self.cloud)
+        self.bk = np.ctypeslib.as_array(bkp, shape=(p.n, rows, 2, p.N)) if bkp else None
+        self.ksk = np.ctypeslib.as_array(kskp, shape=(p.N, p.ks_t, 1 << p.ks_basebit, p.n + 1)) if kskp else None
         self.lwe_key = np.ctypeslib.as_array(sk.contents.lwe_key, shape=(p.n,))
         self.tlwe_key = np.ctypeslib.as_array(sk.contents.tlwe_key, shape=(p.N,))
 
@@ -145,6 +147,17 @@ class KeySet:
         L = load_library()
         params = L.new_default_gate_bootstrapping_parameters(minimum_lambda)
         return cls(params, L.peba1_new_secret_keyset_seeded(params, seed))
+
+    @classmethod
+    def placeholder(cls, minimum_lambda: int = 128) -> "KeySet":
+        """A replica's keyset: no key material on the host, device keys arrive by NCCL broadcast."""
+        L = load_library()
+        params = L.new_default_gate_bootstrapping_parameters(minimum_lambda)
+        return cls(params, L.peba1_new_placeholder_keyset(params))
+
+    def cuda_context(self) -> int:
+        """Handle of the libpeba1_cuda context behind this keyset (created on first use)."""
+        return self.L.peba1_cuda_context_of(self.cloud)
 
     def encrypt(self, bits, seed: int) -> np.ndarray:
         bits = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)

@@ -22,6 +22,7 @@ def env():
     ks = H.KeySet.generate(128, seed=7)
     sim.keyset = ks
     yield L, ks, sim
+    L.peba1_host_set_test_backend(None)
 
 
 def run(env, fn):

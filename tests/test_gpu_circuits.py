@@ -1,0 +1,145 @@
+"""GPU tests of the whole stack: TFHE-compatible front end + Math.h circuits (libpeba1_tfhe.so) on libpeba1_cuda.
+
+Decrypted results are checked against native integer arithmetic (the reference's own self-test comparisons,
+src/main.cpp:320,352,383,422,456,578) and raw output ciphertexts against a faithful per-gate evaluation of the same
+DAG on the CPU oracle (tests/oracle_backend.py) — bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from peba1_b200 import tfhe_host as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_keys():
+    H.load_library().peba1_host_set_test_backend(None)
+    ks = H.KeySet.generate(128, seed=42)
+    yield ks
+
+
+@pytest.fixture(scope="module")
+def cpu_twin(gpu_keys, oracle):
+    """the same key material behind an oracle-backed engine"""
+    from oracle_backend import OracleBackend
+    K = oracle.Keys.from_arrays(oracle.default_params(128), gpu_keys.lwe_key, gpu_keys.tlwe_key, gpu_keys.bk,
+                                gpu_keys.ksk)
+    be = OracleBackend(K)
+    be.install()
+    L = H.load_library()
+    p = L.new_default_gate_bootstrapping_parameters(128)
+    i32p = C.POINTER(C.c_int32)
+    sk = L.peba1_new_keyset_from_arrays(p, gpu_keys.lwe_key.ctypes.data_as(i32p), gpu_keys.tlwe_key.ctypes.data_as(i32p),
+                                        gpu_keys.bk.ctypes.data_as(i32p), gpu_keys.ksk.ctypes.data_as(i32p))
+    twin = H.KeySet(p, sk)
+    # force the engine creation while the oracle backend is installed, then restore the product default
+    tmp = twin.new_array(2)
+    L.bootsAND(twin.at(tmp, 0), twin.at(tmp, 0), twin.at(tmp, 1), twin.cloud)
+    twin.get_words(tmp, 1)
+    OracleBackend.uninstall()
+    yield twin
+    K.close()
+
+
+def test_uses_the_gpu(gpu_keys):
+    L = H.load_library()
+    assert L.peba1_cuda_context_of(gpu_keys.cloud)
+    maps = open("/proc/self/maps").read()
+    assert "libpeba1_cuda.so" in maps and "libpeba1_tfhe.so" in maps
+
+
+def test_add8_values_and_raw_parity(gpu_keys, cpu_twin):
+    L = H.load_library()
+    rng = np.random.default_rng(1)
+    for trial in range(2):
+        x, y = (int(v) for v in rng.integers(0, 256, size=2))
+        wa = gpu_keys.encrypt([(x >> i) & 1 for i in range(8)], 100 + trial)
+        wb = gpu_keys.encrypt([(y >> i) & 1 for i in range(8)], 200 + trial)
+        outs = []
+        for ks in (gpu_keys, cpu_twin):
+            a, b, r, c = ks.new_array(8), ks.new_array(8), ks.new_array(8), ks.new_array(1)
+            ks.set_words(a, wa); ks.set_words(b, wb)
+            L.peba1_math_add(r, a, b, c, 8, ks.cloud)
+            outs.append(np.concatenate([ks.get_words(r, 8), ks.get_words(c, 1)]))
+            for arr, n in ((a, 8), (b, 8), (r, 8), (c, 1)):
+                ks.free_array(n, arr)
+        assert np.array_equal(outs[0], outs[1])                      # raw ciphertext words, GPU == per-gate oracle
+        bits = gpu_keys.decrypt(outs[0])
+        assert sum(int(v) << i for i, v in enumerate(bits)) == x + y  # 9 bits incl. carry
+
+
+def test_sub_and_minimum_raw_parity(gpu_keys, cpu_twin):
+    L = H.load_library()
+    x, y = 77, 0                                                      # exercises quirk Q1 (b = 0)
+    wa = gpu_keys.encrypt([(x >> i) & 1 for i in range(8)], 301)
+    wb = gpu_keys.encrypt([(y >> i) & 1 for i in range(8)], 302)
+    outs = []
+    for ks in (gpu_keys, cpu_twin):
+        a, b, r = ks.new_array(8), ks.new_array(8), ks.new_array(9)
+        m, bit = ks.new_array(8), ks.new_array(8)
+        ks.set_words(a, wa); ks.set_words(b, wb)
+        L.peba1_batch_begin()
+        L.peba1_math_sub(r, a, b, 8, ks.cloud)
+        L.peba1_math_minimum(m, bit, a, b, 8, ks.cloud)               # MUX path: 2 bootstraps + 1 keyswitch
+        L.peba1_batch_end()
+        outs.append(np.concatenate([ks.get_words(r, 9), ks.get_words(m, 8), ks.get_words(bit, 1)]))
+        for arr, n in ((a, 8), (b, 8), (r, 9), (m, 8), (bit, 8)):
+            ks.free_array(n, arr)
+    assert np.array_equal(outs[0], outs[1])
+    bits = gpu_keys.decrypt(outs[0])
+    val = lambda bs: sum(int(v) << i for i, v in enumerate(bs))
+    assert val(bits[:9]) == 256 - 77 and val(bits[9:17]) == 0 and bits[17] == 1
+
+
+def test_multiply8_batch_of_instances(gpu_keys):
+    """BASELINE config 3 shape at reduced instance count: 32 multipliers batched per level (81 launches pairs)."""
+    L = H.load_library()
+    n = 32
+    rng = np.random.default_rng(2)
+    xs, ys = rng.integers(0, 256, size=n), rng.integers(0, 256, size=n)
+    A = [gpu_keys.encrypt_int(int(x), 8, 1000 + i) for i, x in enumerate(xs)]
+    B = [gpu_keys.encrypt_int(int(y), 8, 2000 + i) for i, y in enumerate(ys)]
+    R = [gpu_keys.new_array(23) for _ in range(n)]
+    s0 = gpu_keys.stats()
+    L.peba1_batch_begin()
+    for i in range(n):
+        L.peba1_math_multiply(R[i], A[i], B[i], 8, 0, gpu_keys.cloud)
+    L.peba1_batch_end()
+    s1 = gpu_keys.stats()
+    assert s1.gates - s0.gates == 1296 * n and s1.levels - s0.levels == 81
+    for i in range(n):
+        assert gpu_keys.decrypt_int(R[i], 23) == int(xs[i]) * int(ys[i])          # main.cpp:456
+    for i in range(n):
+        gpu_keys.free_array(8, A[i]); gpu_keys.free_array(8, B[i]); gpu_keys.free_array(23, R[i])
+
+
+def test_face_match_function_f_and_g(gpu_keys):
+    """One full-size face match (128 slots x 8 bits, 215,544 bootstraps) + Function_g, as main.cpp:513-581 does."""
+    L = H.load_library()
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 255, size=128)
+    probe = (t + 1) % 256
+    def vec(values, seed):
+        arrs = [gpu_keys.encrypt_int(int(v), 8, seed + i) for i, v in enumerate(values)]
+        return arrs, (C.POINTER(H.LweSample) * len(arrs))(*arrs)
+    ta, tp = vec(t, 5000)
+    pa, pp = vec(probe, 6000)
+    for bound, expect in ((100, 1), (128, 0)):                        # distance is exactly 128
+        eb = gpu_keys.encrypt_int(bound, 24, 7000)
+        rb = gpu_keys.new_array(24)
+        s0 = gpu_keys.stats()
+        L.peba1_math_function_f(rb, pp, tp, 128, eb, 8, gpu_keys.cloud)
+        s1 = gpu_keys.stats()
+        assert (s1.gates - s0.gates, s1.pbs - s0.pbs, s1.levels - s0.levels) == (215496, 215544, 377)
+        assert gpu_keys.decrypt_int(rb, 24) == expect
+        r0, r1 = 0x3C, 0xA7
+        e0, e1 = gpu_keys.encrypt_int(r0, 8, 8000), gpu_keys.encrypt_int(r1, 8, 8001)
+        y = gpu_keys.new_array(9)
+        L.peba1_math_function_g(y, rb, e0, e1, 8, gpu_keys.cloud)
+        assert gpu_keys.decrypt_int(y, 8) == (r1 if expect else (-r0) % 256)   # main.cpp:578 (+ Q1)
+        gpu_keys.free_array(24, eb); gpu_keys.free_array(24, rb); gpu_keys.free_array(9, y)
+        gpu_keys.free_array(8, e0); gpu_keys.free_array(8, e1)
+    for arr in ta + pa:
+        gpu_keys.free_array(8, arr)
