@@ -142,56 +142,19 @@ class _DevPtr:
 
 def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np):
     """Encrypted face matches/s (BASELINE metric, second half): Function_f = 128-dim 8-bit squared distance + 24-bit
-    threshold compare, one probe against `T` templates per GPU, all templates of a rank recorded into ONE batch so each
-    of the 377 circuit levels is one launch pair.  Rank 0 plays the client (encrypts, decrypts); template ciphertexts
-    are scattered and the encrypted match bits gathered with NCCL."""
-    import ctypes as C
-    from peba1_b200 import tfhe_host as H
-    L = H.load_library()
+    threshold compare, one probe against `T` templates per GPU (peba1_b200/gallery.py).  Timed: recording + the 377
+    batched levels + the NCCL all-gather of the encrypted match bits; not timed: client-side encryption and scatter."""
+    from peba1_b200 import gallery as G
     T = args.face_templates
     slots, bits, words = 128, 8, ks.words
     dev = f"cuda:{local}"
-    rng = np.random.default_rng(2024)
-    probe = rng.integers(1, 256, size=slots)                     # no zero byte: reference quirk Q1 stays silent
-    gallery = rng.integers(0, 256, size=(world * T, slots))
-    planted = rng.random(world * T) < 0.25                        # a quarter of the gallery are near-copies
-    gallery[planted] = np.clip(probe + rng.integers(-2, 3, size=(int(planted.sum()), slots)), 0, 255)
-    dist2 = ((gallery.astype(np.int64) - probe) ** 2).sum(axis=1)
-    bound = 128 * 4
-    expect = (dist2 > bound).astype(np.int64)                     # comparator polarity Q3: 1 iff distance > bound
-
-    def bits_of(vec, nb):
-        return np.array([[(int(v) >> j) & 1 for j in range(nb)] for v in vec]).reshape(-1)
-
-    probe_t = torch.empty((slots * bits, words), dtype=torch.int32, device=dev)
-    bound_t = torch.empty((24, words), dtype=torch.int32, device=dev)
-    mine_t = torch.empty((T, slots * bits, words), dtype=torch.int32, device=dev)
+    bound = 512
+    probe, gal, expect = G.synthetic_gallery(world * T, slots, bound=bound)
+    client = None
     if rank == 0:
-        probe_t.copy_(torch.from_numpy(ks.encrypt(bits_of(probe, bits), 501)))
-        bound_t.copy_(torch.from_numpy(ks.encrypt(bits_of([bound], 24), 502)))
-        allg = ks.encrypt(bits_of(gallery.reshape(-1), bits), 503).reshape(world, T, slots * bits, words)
-        chunks = [torch.from_numpy(np.ascontiguousarray(allg[r])).to(dev) for r in range(world)]
-    if dist is not None:
-        dist.broadcast(probe_t, 0)
-        dist.broadcast(bound_t, 0)
-        dist.scatter(mine_t, chunks if rank == 0 else None, src=0)
-    else:
-        mine_t.copy_(chunks[0])
-    probe_w, bound_w, mine_w = probe_t.cpu().numpy(), bound_t.cpu().numpy(), mine_t.cpu().numpy()
-
-    LSP = C.POINTER(H.LweSample)
-    def vec(wordsarr):
-        arrs = []
-        for i in range(slots):
-            a = ks.new_array(bits)
-            ks.set_words(a, wordsarr[i * bits:(i + 1) * bits])
-            arrs.append(a)
-        return arrs, (LSP * slots)(*arrs)
-    pa, pp = vec(probe_w)
-    eb = ks.new_array(24)
-    ks.set_words(eb, bound_w)
-    tv = [vec(mine_w[t]) for t in range(T)]
-    rb = [ks.new_array(24) for _ in range(T)]
+        client = (ks.encrypt(G.bits_of(probe, bits), 501), ks.encrypt(G.bits_of([bound], 24), 502),
+                  ks.encrypt(G.bits_of(gal.reshape(-1), bits), 503))
+    probe_w, bound_w, mine_w = G.distribute(dist, rank, world, dev, torch, words, slots, bits, T, client)
 
     def barrier():
         if dist is not None:
@@ -201,15 +164,8 @@ def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np):
     c0 = eng.stats().launches
     barrier()
     t0 = time.perf_counter()
-    L.peba1_batch_begin()
-    for t in range(T):
-        L.peba1_math_function_f(rb[t], pp, tv[t][1], slots, eb, bits, ks.cloud)
-    L.peba1_batch_end()                                           # 377 levels, each one blind-rotation + keyswitch launch
-    out = np.stack([ks.get_words(rb[t], 1)[0] for t in range(T)])
-    out_t = torch.from_numpy(out).to(dev)
-    gathered = [torch.empty_like(out_t) for _ in range(world)] if dist is not None else [out_t]
-    if dist is not None:
-        dist.all_gather(gathered, out_t)                          # encrypted match bits over NVLink
+    out = G.match_templates(ks, probe_w, bound_w, mine_w, slots, bits)
+    allout = G.gather_match_bits(dist, world, dev, torch, out)       # encrypted match bits over NVLink
     barrier()
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -223,7 +179,7 @@ def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np):
            "workload": f"Function_f (128-dim 8-bit squared distance + 24-bit threshold), 1 probe vs {world * T} templates, "
                        "215,544 bootstraps per match", "timing": "wall clock incl. host recording, max over ranks"}
     if rank == 0:
-        got = ks.decrypt(torch.stack(gathered).cpu().numpy().reshape(-1, words))
+        got = ks.decrypt(allout)
         res["verified"] = bool(np.array_equal(got, expect))
         res["matches_found"] = int((got == 0).sum())
     return res

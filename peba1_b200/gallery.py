@@ -1,0 +1,105 @@
+"""1:N encrypted identification over a sharded gallery (BASELINE configs[3] and [4]).
+
+One process per GPU.  Rank 0 plays the client: it encrypts the probe, the 24-bit bound and the gallery.  The probe
+and the bound are broadcast, template ciphertexts are scattered (each rank keeps `T` templates), every rank records
+`Function_f` for all of its templates into ONE batch (so each of the 377 circuit levels is one launch pair), and the
+encrypted match bits (one 2,524-byte ciphertext per template) are all-gathered.  No collective sits inside the hot
+loop.  Works with any torch.distributed backend (NCCL on GPUs, gloo in the CPU tests) or without one (world = 1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import tfhe_host as H
+
+
+def shard_bounds(total: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of `total` templates for `rank` (sizes differ by at most one)."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def bits_of(values, nbits: int) -> np.ndarray:
+    v = np.asarray(values, dtype=np.int64).reshape(-1, 1)
+    return ((v >> np.arange(nbits)) & 1).reshape(-1).astype(np.int32)
+
+
+def synthetic_gallery(total: int, slots: int = 128, seed: int = 2024, planted: float = 0.25, bound: int = 512):
+    """Probe, gallery and expected comparator bits.  The probe has no zero byte, so the reference's subtraction defect
+    (wrong when the subtrahend is 0) stays silent; a fraction of the gallery are near-copies of the
+    probe.  Polarity (Q3): the bit is 1 iff squared distance > bound."""
+    rng = np.random.default_rng(seed)
+    probe = rng.integers(1, 256, size=slots)
+    gallery = rng.integers(0, 256, size=(total, slots))
+    mask = rng.random(total) < planted
+    gallery[mask] = np.clip(probe + rng.integers(-2, 3, size=(int(mask.sum()), slots)), 0, 255)
+    dist2 = ((gallery.astype(np.int64) - probe) ** 2).sum(axis=1)
+    return probe, gallery, (dist2 > bound).astype(np.int64)
+
+
+def distribute(dist, rank: int, world: int, device, torch, words: int, slots: int, bits: int, per_rank: int,
+               client=None):
+    """client = (probe_words [slots*bits, words], bound_words [24, words], gallery_words [world*per_rank, slots*bits,
+    words]) on rank 0, None elsewhere.  Returns this rank's (probe, bound, templates) as numpy arrays."""
+    probe_t = torch.empty((slots * bits, words), dtype=torch.int32, device=device)
+    bound_t = torch.empty((24, words), dtype=torch.int32, device=device)
+    mine_t = torch.empty((per_rank, slots * bits, words), dtype=torch.int32, device=device)
+    chunks = None
+    if rank == 0:
+        pw, bw, gw = client
+        probe_t.copy_(torch.from_numpy(np.ascontiguousarray(pw)))
+        bound_t.copy_(torch.from_numpy(np.ascontiguousarray(bw)))
+        gw = np.ascontiguousarray(gw).reshape(world, per_rank, slots * bits, words)
+        chunks = [torch.from_numpy(gw[r]).to(device) for r in range(world)]
+    if dist is not None and world > 1:
+        dist.broadcast(probe_t, 0)
+        dist.broadcast(bound_t, 0)
+        dist.scatter(mine_t, chunks, src=0)
+    else:
+        mine_t.copy_(chunks[0])
+    return probe_t.cpu().numpy(), bound_t.cpu().numpy(), mine_t.cpu().numpy()
+
+
+def match_templates(ks: "H.KeySet", probe_w, bound_w, templates_w, slots: int = 128, bits: int = 8) -> np.ndarray:
+    """Function_f(probe, template_t, bound) for every local template, one batch; returns the comparator-bit
+    ciphertexts [T, words]."""
+    L = H.load_library()
+    LSP = C.POINTER(H.LweSample)
+
+    def vec(w):
+        arrs = []
+        for i in range(slots):
+            a = ks.new_array(bits)
+            ks.set_words(a, w[i * bits:(i + 1) * bits])
+            arrs.append(a)
+        return arrs, (LSP * slots)(*arrs)
+    pa, pp = vec(probe_w)
+    eb = ks.new_array(24)
+    ks.set_words(eb, bound_w)
+    T = templates_w.shape[0]
+    tv = [vec(templates_w[t]) for t in range(T)]
+    rb = [ks.new_array(24) for _ in range(T)]
+    L.peba1_batch_begin()
+    for t in range(T):
+        L.peba1_math_function_f(rb[t], pp, tv[t][1], slots, eb, bits, ks.cloud)
+    L.peba1_batch_end()
+    out = np.stack([ks.get_words(rb[t], 1)[0] for t in range(T)]) if T else np.zeros((0, ks.words), np.int32)
+    for arrs, _ in tv + [(pa, pp)]:
+        for a in arrs:
+            ks.free_array(bits, a)
+    for a in rb + [eb]:
+        ks.free_array(24, a)
+    return out
+
+
+def gather_match_bits(dist, world: int, device, torch, local_out: np.ndarray) -> np.ndarray:
+    """All-gather of the encrypted match bits; returns [world*T, words] (rank-major) on every rank."""
+    t = torch.from_numpy(np.ascontiguousarray(local_out)).to(device)
+    if dist is None or world == 1:
+        return local_out
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return torch.cat(parts).cpu().numpy()
