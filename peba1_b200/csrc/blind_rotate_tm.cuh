@@ -1,0 +1,258 @@
+// blind_rotate_tm.cuh — blind rotation with the MAC accumulators and the per-thread twiddles in TENSOR MEMORY.
+//
+// Why: the first version (blind_rotate.cuh) keeps, per thread, 64 registers of frequency-domain accumulators and 64
+// of twiddles, which caps the kernel at 168-255 registers = 8-12 warps per SM, and ncu shows it latency-bound (2-3
+// warps per scheduler, "short scoreboard" on every shared-memory exchange).  Shared memory and L1 are the busiest
+// pipe already, so spilling there is no option.  Blackwell's 256 KB tensor memory is a separate datapath that the
+// kernel does not use otherwise (there is no MMA in this algorithm): tcgen05.st / tcgen05.ld in the 32x32b shape give
+// every thread a private row of 32-bit cells (measured: 570 B/clk/SM load+store with 16 warps; this kernel needs
+// ~140).  With accumulators and twiddles there the kernel fits 128 registers: 8 teams = 16 warps per SM.
+//
+// TMEM layout (512 columns allocated, one CTA per SM).  Lane quarter q = warp % 4 is fixed by the hardware; the four
+// warps w, w+4, w+8, w+12 that share a quarter use different column blocks:
+//   columns [64*(warp/4), +64)   accumulators of this thread: [c (2)][k2 (8)][re.lo re.hi im.lo im.hi]
+//   columns [256, 288)           tw1[8] of thread tid = 32*(warp&1) + lane   (the same for all warps of a quarter)
+//   columns [288, 320)           tw2[8]
+//
+// Same arithmetic, in the same order, as blind_rotate.cuh (bit-exact vs the exact-integer oracle); __host__
+// __device__ so csrc/emu_team.cu can run it on CPU threads (tensor memory emulated by a per-thread array).
+#pragma once
+
+#include "blind_rotate.cuh"
+
+namespace peba1 {
+
+constexpr int kTmSums = 0;      // + 64 * (warp / 4)
+constexpr int kTmTw1 = 256;
+constexpr int kTmTw2 = 288;
+
+// Shared memory of one team in this version: ONE cross-team exchange buffer (two barriers per transform instead of
+// double buffering) so that 8 teams fit: 8 KB + 8 KB + 8 KB + 1.25 KB = 25.25 KB per team.
+struct __align__(16) TeamSmemTm {
+    double2  ex1[kM];
+    double2  ex2[kM];
+    int32_t  acc[2][kN];
+    uint16_t bara[640];
+};
+
+PEBA1_HD double2 words_to_c(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    return make_double2(__hiloint2double((int)b, (int)a), __hiloint2double((int)d, (int)c));
+#else
+    uint64_t re = ((uint64_t)b << 32) | a, im = ((uint64_t)d << 32) | c;
+    double2 r;
+    memcpy(&r.x, &re, 8);
+    memcpy(&r.y, &im, 8);
+    return r;
+#endif
+}
+PEBA1_HD void c_to_words(double2 v, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+#ifdef __CUDA_ARCH__
+    a = (uint32_t)__double2loint(v.x); b = (uint32_t)__double2hiint(v.x);
+    c = (uint32_t)__double2loint(v.y); d = (uint32_t)__double2hiint(v.y);
+#else
+    uint64_t re, im;
+    memcpy(&re, &v.x, 8);
+    memcpy(&im, &v.y, 8);
+    a = (uint32_t)re; b = (uint32_t)(re >> 32); c = (uint32_t)im; d = (uint32_t)(im >> 32);
+#endif
+}
+
+// 8 complex values <-> 32 tensor-memory cells
+template <class Env>
+PEBA1_HD void tm_load8(Env& env, int col, double2 (&v)[8]) {
+    uint32_t w[32];
+    env.tmem_ld32(col, w);
+    env.tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = words_to_c(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+template <class Env>
+PEBA1_HD void tm_store8(Env& env, int col, const double2 (&v)[8]) {
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c_to_words(v[j], w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    env.tmem_st32(col, w);
+}
+
+// Forward transform; twiddles come from tensor memory right before their use.
+template <class Env>
+PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
+    const int tid = env.tid;
+#pragma unroll
+    for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
+    radix8<false>(x);
+    {
+        double2 tw[8];
+        tm_load8(env, kTmTw1, tw);
+        env.team_sync();  // every reader of the previous transform's ex1 is done
+#pragma unroll
+        for (int k0 = 0; k0 < 8; ++k0) sm.ex1[64 * k0 + tid] = cmul(x[k0], tw[k0]);
+    }
+    env.team_sync();
+    const int hi = tid >> 3, lo = tid & 7;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) x[b] = sm.ex1[64 * hi + 8 * b + lo];
+    radix8<false>(x);
+    {
+        double2 tw[8];
+        tm_load8(env, kTmTw2, tw);
+        sm.ex2[64 * hi + lo] = x[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)] = cmul(x[k1], tw[k1]);
+    }
+    env.warp_sync();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] = sm.ex2[64 * hi + 8 * lo + (c ^ lo)];
+    radix8<false>(x);
+}
+
+template <class Env>
+PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
+    const int tid = env.tid;
+    const int hi = tid >> 3, lo = tid & 7;
+    radix8<true>(x);
+    {
+        double2 tw[8];
+        tm_load8(env, kTmTw2, tw);
+        env.warp_sync();  // previous readers of ex2 are done
+        sm.ex2[64 * hi + 8 * lo + lo] = x[0];
+#pragma unroll
+        for (int c = 1; c < 8; ++c) sm.ex2[64 * hi + 8 * lo + (c ^ lo)] = cmul_conj(x[c], tw[c]);
+    }
+    env.warp_sync();
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) x[k1] = sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)];
+    radix8<true>(x);
+    env.team_sync();  // previous readers of ex1 are done
+#pragma unroll
+    for (int b = 0; b < 8; ++b) sm.ex1[64 * hi + 8 * b + lo] = x[b];
+    env.team_sync();
+    {
+        double2 tw[8];
+        tm_load8(env, kTmTw1, tw);
+#pragma unroll
+        for (int k0 = 0; k0 < 8; ++k0) x[k0] = cmul_conj(sm.ex1[64 * k0 + tid], tw[k0]);
+    }
+    radix8<true>(x);
+#pragma unroll
+    for (int a = 1; a < 8; ++a) x[a] = cmul_conj(x[a], w32(a));
+}
+
+// Writes this thread's twiddles into tensor memory (called once per kernel by the warps with warp/4 == 0).
+template <class Env>
+PEBA1_HD void tm_store_twiddles(Env& env, const TeamTwiddles& tw) {
+    tm_store8(env, kTmTw1, tw.tw1);
+    tm_store8(env, kTmTw2, tw.tw2);
+    env.tmem_wait_st();
+}
+
+template <int L, int BGBIT, class Env>
+PEBA1_HD void blind_rotate_team_tm(Env& env, TeamSmemTm& sm, const double2* __restrict__ bkfft, int n,
+                                   const int32_t* __restrict__ pool, int64_t pool_stride, PbsJob job,
+                                   int32_t* __restrict__ u_out) {
+    constexpr int ROWS = 2 * L;
+    constexpr uint32_t HALF_BG = 1u << (BGBIT - 1);
+    constexpr uint32_t MASK_BG = (1u << BGBIT) - 1;
+    uint32_t offset = 0;
+#pragma unroll
+    for (int p = 1; p <= L; ++p) offset += HALF_BG << (32 - p * BGBIT);
+    const int tid = env.tid;
+    const int sums = env.sums_col;  // kTmSums + 64 * (warp / 4)
+
+    // ---- prologue + mod-switch (identical to blind_rotate_team)
+    for (int w = tid; w <= n; w += kTeam) {
+        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
+        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
+        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
+        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
+    }
+    env.team_sync();
+    {
+        const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);
+        const int32_t mu = 1 << 29;
+        for (int j = tid; j < kN; j += kTeam) {
+            const int idx = (j - rot) & (2 * kN - 1);
+            sm.acc[0][j] = 0;
+            sm.acc[1][j] = (idx & kN) ? -mu : mu;
+        }
+    }
+    env.team_sync();
+
+    for (int i = 0; i < n; ++i) {
+        const int abar = sm.bara[i];
+        if (abar == 0) continue;
+        uint32_t tv[16];
+#pragma unroll 1
+        for (int r = 0; r < ROWS; ++r) {
+            const int poly = r >= L ? 1 : 0;
+            const int p = r - poly * L;
+            if (p == 0) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
+                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
+                }
+            }
+            const int shift = 32 - (p + 1) * BGBIT;
+            double2 x[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int32_t dr = (int32_t)((tv[a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
+                const int32_t di = (int32_t)((tv[8 + a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
+                x[a] = make_double2(i2d(dr), i2d(di));
+            }
+            team_fft_forward_tm(env, x, sm);
+            // pointwise MAC against BK_i row r, accumulators in tensor memory, 4 bins of one column at a time
+            const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t w[16];
+                    double2 b[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) b[q] = env.ldg2(bk + (size_t)(2 * (4 * half + q) + c) * 64);
+                    double2 s[4];
+                    if (r > 0) {
+                        if (c == 0 && half == 0) env.tmem_wait_st();  // the previous row's stores have landed
+                        env.tmem_ld16(sums + 32 * c + 16 * half, w);
+                        env.tmem_wait_ld();
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) s[q] = words_to_c(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) s[q] = make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        cfma(s[q], x[4 * half + q], b[q]);
+                        c_to_words(s[q], w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+                    }
+                    env.tmem_st16(sums + 32 * c + 16 * half, w);
+                }
+            }
+        }
+        env.tmem_wait_st();
+        // inverse transforms and accumulator update (round to nearest, wrap mod 2^32)
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            double2 s[8];
+            tm_load8(env, sums + 32 * c, s);
+            team_fft_inverse_tm(env, s, sm);
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                sm.acc[c][64 * a + tid] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid] + d2u_rn(s[a].x));
+                sm.acc[c][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid + 512] + d2u_rn(s[a].y));
+            }
+        }
+        env.team_sync();
+    }
+
+    for (int j = tid; j < kN; j += kTeam)
+        u_out[j] = (j == 0) ? sm.acc[0][0] : (int32_t)(0u - (uint32_t)sm.acc[0][kN - j]);
+    if (tid == 0) u_out[kN] = sm.acc[1][0];
+    env.team_sync();
+}
+
+}  // namespace peba1

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <vector>
 #include "blind_rotate.cuh"
+#include "blind_rotate_tm.cuh"
 #include "twiddles_host.h"
 
 using namespace peba1;
@@ -21,10 +22,20 @@ struct HostEnv {
     void warp_sync() { pthread_barrier_wait(warp); }
     int32_t ldg(const int32_t* p) const { return *p; }
     double2 ldg2(const double2* p) const { return *p; }
+    // tensor memory of the tensor-memory variant, emulated as a private array of 32-bit cells per thread
+    int sums_col = 0;
+    uint32_t* tm = nullptr;
+    void tmem_ld16(int col, uint32_t (&w)[16]) const { memcpy(w, tm + col, sizeof w); }
+    void tmem_st16(int col, const uint32_t (&w)[16]) const { memcpy(tm + col, w, sizeof w); }
+    void tmem_ld32(int col, uint32_t (&w)[32]) const { memcpy(w, tm + col, sizeof w); }
+    void tmem_st32(int col, const uint32_t (&w)[32]) const { memcpy(tm + col, w, sizeof w); }
+    void tmem_wait_ld() const {}
+    void tmem_wait_st() const {}
 };
 
 struct Shared {
     TeamSmem sm;
+    TeamSmemTm sm_tm;
     TwiddleTables tables;
     pthread_barrier_t team, warp[2];
     // work description
@@ -51,6 +62,20 @@ void* worker(void* p) {
             const int c = q & 1, ir = q >> 1;
             key_transform_team(env, S->sm, tw, S->bk + (size_t)q * kN,
                                S->bkfft + bkfft_index(S->rows, ir / S->rows, ir % S->rows, 0, c, 0));
+        }
+    } else if (S->mode == 2) {
+        std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
+        env.tm = tmem.data();
+        env.sums_col = 64 * (A->tid % 3);  // any column block must work
+        tm_store_twiddles(env, tw);
+        for (int64_t g = 0; g < S->count; ++g) {
+            PbsJob job{0, -1, 0, 1, 0};
+            const int32_t* pool = S->in_ct + (size_t)g * (S->n + 1);
+            int32_t* u = S->u_out + (size_t)g * (kN + 1);
+            if (S->L == 3 && S->Bgbit == 7)
+                blind_rotate_team_tm<3, 7>(env, S->sm_tm, S->bkfft, S->n, pool, S->n + 1, job, u);
+            else
+                blind_rotate_team_tm<2, 10>(env, S->sm_tm, S->bkfft, S->n, pool, S->n + 1, job, u);
         }
     } else {
         for (int64_t g = 0; g < S->count; ++g) {
@@ -100,6 +125,18 @@ int peba1_emu_bootstrap_woks(int L, int Bgbit, int n, const double* bkfft, const
     if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
     Shared* S = new Shared();
     S->mode = 1; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
+    S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+// the tensor-memory variant of the kernel code (blind_rotate_tm.cuh)
+int peba1_emu_bootstrap_woks_tm(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                                int64_t count) {
+    if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
+    Shared* S = new Shared();
+    S->mode = 2; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
     S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
     int rc = run(S);
     delete S;

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -19,6 +20,7 @@
 #include <vector>
 
 #include "blind_rotate.cuh"
+#include "blind_rotate_tm.cuh"
 #include "twiddles_host.h"
 
 using namespace peba1;
@@ -55,6 +57,61 @@ struct DevEnv {
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ int32_t ldg(const int32_t* p) const { return __ldg(p); }
     __device__ __forceinline__ double2 ldg2(const double2* p) const { return __ldg(p); }
+};
+
+// tcgen05 32x32b load/store wrappers (tensor memory used as per-thread scratch; see blind_rotate_tm.cuh)
+#define R8(a, o) "%" #o
+__device__ __forceinline__ void tmem_ld_x16(uint32_t addr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t addr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t addr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t addr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+#undef R8
+
+struct DevEnvTm {
+    int tid;
+    int bar_id;
+    int sums_col;
+    uint32_t tm_base;  // allocation base + this warp's lane quarter
+    __device__ __forceinline__ void team_sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTeam) : "memory"); }
+    __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    __device__ __forceinline__ int32_t ldg(const int32_t* p) const { return __ldg(p); }
+    __device__ __forceinline__ double2 ldg2(const double2* p) const { return __ldg(p); }
+    __device__ __forceinline__ void tmem_ld16(int col, uint32_t (&w)[16]) const { tmem_ld_x16(tm_base + (uint32_t)col, w); }
+    __device__ __forceinline__ void tmem_st16(int col, const uint32_t (&w)[16]) const { tmem_st_x16(tm_base + (uint32_t)col, w); }
+    __device__ __forceinline__ void tmem_ld32(int col, uint32_t (&w)[32]) const { tmem_ld_x32(tm_base + (uint32_t)col, w); }
+    __device__ __forceinline__ void tmem_st32(int col, const uint32_t (&w)[32]) const { tmem_st_x32(tm_base + (uint32_t)col, w); }
+    __device__ __forceinline__ void tmem_wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void tmem_wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
 
 __constant__ TwiddleTables c_tables;
@@ -94,6 +151,49 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     load_twiddles_dev(env.tid, tw);
     blind_rotate_team<L, BGBIT>(env, teams[team], tw, bkfft, n, pool, pool_stride, jobs[g],
                                 u_out + g * (int64_t)kUStride);
+}
+
+// K0+K1, tensor-memory version: 8 teams (512 threads, 16 warps) per CTA, one CTA per SM, <= 128 registers.
+constexpr int kTeamsTm = 8;
+template <int L, int BGBIT>
+__global__ void __launch_bounds__(kTeamsTm* kTeam, 1)
+    pbs_kernel_tm(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
+                  const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TeamSmemTm* teams = reinterpret_cast<TeamSmemTm*>(smem_raw);
+    __shared__ uint32_t tm_alloc_base;
+    const int warp = threadIdx.x >> 5;
+    const int team = threadIdx.x / kTeam;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"l"(
+            (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 64 * (warp >> 2),
+                 tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16)};
+    if ((warp >> 2) == 0) {  // one warp per lane quarter publishes the per-thread twiddles
+        TeamTwiddles tw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            tw.tw1[j] = c_tables.tw1[env.tid][j];
+            tw.tw2[j] = c_tables.tw2[env.tid & 7][j];
+        }
+        tm_store_twiddles(env, tw);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int64_t g = (int64_t)blockIdx.x * kTeamsTm + team;
+    if (g < count)
+        blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
+                                       u_out + g * (int64_t)kUStride);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_alloc_base));
 }
 
 // K3.  One team per key polynomial q = (i*rows + r)*2 + c.
@@ -264,6 +364,7 @@ struct peba1_cuda_ctx {
     size_t h_stage_cap = 0;
     // options
     int teams_per_cta = 6;
+    int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default)
     int64_t max_pbs_per_launch = 1 << 18;
     // stats
     bool timing = false;
@@ -329,11 +430,36 @@ int launch_pbs_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const P
     return 0;
 }
 
+int launch_pbs_tm(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
+                  int32_t* u) {
+    const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
+    const unsigned grid = (unsigned)((count + kTeamsTm - 1) / kTeamsTm);
+    if (c->p.l == 3) {
+        auto k = pbs_kernel_tm<3, 7>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+    } else {
+        auto k = pbs_kernel_tm<2, 10>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+    }
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    return 0;
+}
+
 int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
                int32_t* u) {
     if (count <= 0) return 0;
     if (c->timing) CU(cudaEventRecord(c->ev0, c->stream));
     int rc;
+    if (c->kernel_variant == 1) {
+        rc = launch_pbs_tm(c, pool, stride, jobs, count, u);
+        if (rc) return rc;
+        if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
+        c->stats.pbs += (uint64_t)count;
+        return 0;
+    }
     switch (c->teams_per_cta) {
         case 1: rc = launch_pbs_t<1>(c, pool, stride, jobs, count, u); break;
         case 2: rc = launch_pbs_t<2>(c, pool, stride, jobs, count, u); break;
@@ -438,6 +564,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) == 0 ? 0 : 1;  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
@@ -861,6 +988,11 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         if (value == 0) value = 6;
         if (value < 1 || value > 6) return fail(PEBA1_EINVAL, "teams_per_cta must be 1..6");
         c->teams_per_cta = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "kernel_variant")) {
+        if (value != 0 && value != 1) return fail(PEBA1_EINVAL, "kernel_variant must be 0 or 1");
+        c->kernel_variant = (int)value;
         return 0;
     }
     if (!strcmp(name, "max_pbs_per_launch")) {

@@ -32,3 +32,9 @@ def test_team_bootstrap_matches_exact_oracle(emu, oracle, keys):
                                         tin.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p),
                                         C.c_int64(1)) == 0
     assert np.array_equal(u[0], g["pbs_out"])
+    # the tensor-memory variant (blind_rotate_tm.cuh) on the same input
+    u2 = np.zeros((1, 1025), dtype=np.int32)
+    assert emu.peba1_emu_bootstrap_woks_tm(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
+                                           tin.ctypes.data_as(C.c_void_p), u2.ctypes.data_as(C.c_void_p),
+                                           C.c_int64(1)) == 0
+    assert np.array_equal(u2[0], g["pbs_out"])
