@@ -25,6 +25,7 @@ namespace peba1 {
 constexpr int kTmSums = 0;      // + 64 * (warp / 4)
 constexpr int kTmTw1 = 256;
 constexpr int kTmTw2 = 288;
+constexpr int kTmZero = 320;    // 16 cells of 0.0: the first row of a step "loads" its accumulators from here
 
 // Shared memory of one team in this version: ONE cross-team exchange buffer (two barriers per transform instead of
 // double buffering) so that 8 teams fit: 8 KB + 8 KB + 8 KB + 1.25 KB = 25.25 KB per team.
@@ -79,28 +80,27 @@ PEBA1_HD void tm_store8(Env& env, int col, const double2 (&v)[8]) {
 template <class Env>
 PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
     const int tid = env.tid;
+    uint32_t w[32];
+    env.tmem_ld32(kTmTw1, w);  // in flight while the first pass computes
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
     radix8<false>(x);
-    {
-        double2 tw[8];
-        tm_load8(env, kTmTw1, tw);
-        env.team_sync();  // every reader of the previous transform's ex1 is done
+    env.tmem_wait_ld();
+    env.team_sync();  // every reader of the previous transform's ex1 is done
 #pragma unroll
-        for (int k0 = 0; k0 < 8; ++k0) sm.ex1[64 * k0 + tid] = cmul(x[k0], tw[k0]);
-    }
+    for (int k0 = 0; k0 < 8; ++k0)
+        sm.ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
+    env.tmem_ld32(kTmTw2, w);  // in flight across the barrier, the loads and the second pass
     env.team_sync();
     const int hi = tid >> 3, lo = tid & 7;
 #pragma unroll
     for (int b = 0; b < 8; ++b) x[b] = sm.ex1[64 * hi + 8 * b + lo];
     radix8<false>(x);
-    {
-        double2 tw[8];
-        tm_load8(env, kTmTw2, tw);
-        sm.ex2[64 * hi + lo] = x[0];
+    env.tmem_wait_ld();
+    sm.ex2[64 * hi + lo] = x[0];
 #pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)] = cmul(x[k1], tw[k1]);
-    }
+    for (int k1 = 1; k1 < 8; ++k1)
+        sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
     env.warp_sync();
 #pragma unroll
     for (int c = 0; c < 8; ++c) x[c] = sm.ex2[64 * hi + 8 * lo + (c ^ lo)];
@@ -111,15 +111,16 @@ template <class Env>
 PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
     const int tid = env.tid;
     const int hi = tid >> 3, lo = tid & 7;
+    uint32_t w[32];
+    env.tmem_ld32(kTmTw2, w);
     radix8<true>(x);
-    {
-        double2 tw[8];
-        tm_load8(env, kTmTw2, tw);
-        env.warp_sync();  // previous readers of ex2 are done
-        sm.ex2[64 * hi + 8 * lo + lo] = x[0];
+    env.tmem_wait_ld();
+    env.warp_sync();  // previous readers of ex2 are done
+    sm.ex2[64 * hi + 8 * lo + lo] = x[0];
 #pragma unroll
-        for (int c = 1; c < 8; ++c) sm.ex2[64 * hi + 8 * lo + (c ^ lo)] = cmul_conj(x[c], tw[c]);
-    }
+    for (int c = 1; c < 8; ++c)
+        sm.ex2[64 * hi + 8 * lo + (c ^ lo)] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+    env.tmem_ld32(kTmTw1, w);
     env.warp_sync();
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) x[k1] = sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)];
@@ -128,12 +129,10 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
 #pragma unroll
     for (int b = 0; b < 8; ++b) sm.ex1[64 * hi + 8 * b + lo] = x[b];
     env.team_sync();
-    {
-        double2 tw[8];
-        tm_load8(env, kTmTw1, tw);
+    env.tmem_wait_ld();
 #pragma unroll
-        for (int k0 = 0; k0 < 8; ++k0) x[k0] = cmul_conj(sm.ex1[64 * k0 + tid], tw[k0]);
-    }
+    for (int k0 = 0; k0 < 8; ++k0)
+        x[k0] = cmul_conj(sm.ex1[64 * k0 + tid], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
     radix8<true>(x);
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul_conj(x[a], w32(a));
@@ -144,6 +143,10 @@ template <class Env>
 PEBA1_HD void tm_store_twiddles(Env& env, const TeamTwiddles& tw) {
     tm_store8(env, kTmTw1, tw.tw1);
     tm_store8(env, kTmTw2, tw.tw2);
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0u;
+    env.tmem_st16(kTmZero, z);
     env.tmem_wait_st();
 }
 
@@ -203,35 +206,44 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, TeamSmemTm& sm, const double2* __re
                 x[a] = make_double2(i2d(dr), i2d(di));
             }
             team_fft_forward_tm(env, x, sm);
-            // pointwise MAC against BK_i row r, accumulators in tensor memory, 4 bins of one column at a time
+            // pointwise MAC against BK_i row r.  Accumulators live in tensor memory; chunk q = (column c, 4 bins).
+            // Software pipeline: the accumulators and key values of chunk q+1 are in flight while chunk q is
+            // multiplied.  Row 0 reads its accumulators from the zero block (no branch, no register clearing).
             const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t w[16];
-                    double2 b[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) b[q] = env.ldg2(bk + (size_t)(2 * (4 * half + q) + c) * 64);
-                    double2 s[4];
-                    if (r > 0) {
-                        if (c == 0 && half == 0) env.tmem_wait_st();  // the previous row's stores have landed
-                        env.tmem_ld16(sums + 32 * c + 16 * half, w);
-                        env.tmem_wait_ld();
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) s[q] = words_to_c(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) s[q] = make_double2(0.0, 0.0);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        cfma(s[q], x[4 * half + q], b[q]);
-                        c_to_words(s[q], w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-                    }
-                    env.tmem_st16(sums + 32 * c + 16 * half, w);
-                }
-            }
+            if (r > 0) env.tmem_wait_st();  // the previous row's stores have landed
+            uint32_t w0[16], w1[16];
+            double2 b0[4], b1[4];
+            const int zsel = r > 0 ? 1 : 0;
+#define PEBA1_CHUNK_COL(q) (zsel ? sums + 32 * ((q) >> 1) + 16 * ((q) & 1) : kTmZero)
+#define PEBA1_CHUNK_LDG(q, b)                                                                              \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e)                                                          \
+        b[e] = env.ldg2(bk + (size_t)(2 * (4 * ((q) & 1) + e) + ((q) >> 1)) * 64);
+#define PEBA1_CHUNK_MAC(q, w, b)                                                                           \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
+        double2 sacc = words_to_c(w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                      \
+        cfma(sacc, x[4 * ((q) & 1) + e], b[e]);                                                            \
+        c_to_words(sacc, w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                               \
+    }                                                                                                      \
+    env.tmem_st16(sums + 32 * ((q) >> 1) + 16 * ((q) & 1), w);
+            env.tmem_ld16(PEBA1_CHUNK_COL(0), w0);
+            PEBA1_CHUNK_LDG(0, b0)
+            env.tmem_wait_ld();
+            env.tmem_ld16(PEBA1_CHUNK_COL(1), w1);
+            PEBA1_CHUNK_LDG(1, b1)
+            PEBA1_CHUNK_MAC(0, w0, b0)
+            env.tmem_wait_ld();
+            env.tmem_ld16(PEBA1_CHUNK_COL(2), w0);
+            PEBA1_CHUNK_LDG(2, b0)
+            PEBA1_CHUNK_MAC(1, w1, b1)
+            env.tmem_wait_ld();
+            env.tmem_ld16(PEBA1_CHUNK_COL(3), w1);
+            PEBA1_CHUNK_LDG(3, b1)
+            PEBA1_CHUNK_MAC(2, w0, b0)
+            env.tmem_wait_ld();
+            PEBA1_CHUNK_MAC(3, w1, b1)
+#undef PEBA1_CHUNK_COL
+#undef PEBA1_CHUNK_LDG
+#undef PEBA1_CHUNK_MAC
         }
         env.tmem_wait_st();
         // inverse transforms and accumulator update (round to nearest, wrap mod 2^32)
