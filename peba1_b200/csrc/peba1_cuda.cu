@@ -214,54 +214,87 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
                        bkfft + bkfft_index(rows, (int)(ir / rows), (int)(ir % rows), 0, c, 0));
 }
 
-// K2.  One CTA per keyswitch job.  Thread t owns output words 4t..4t+3 (row stride is a multiple of 4 words).
-// KSK device layout: [i][j][d-1][stride] (the all-zero digit-0 rows are dropped).
+// K2.  Keyswitch.  KSK device layout: [i][j][d-1][stride] (the all-zero digit-0 rows are dropped).
+// One CTA of 160 threads handles G ciphertexts; thread t owns output words 4t..4t+3 of ALL G of them (4G accumulator
+// registers; the row stride is a multiple of 4 words).  For every digit position (i, j) each ciphertext with a
+// non-zero digit streams one 2.5 KB key row (ld.global.nc.v4).  The G requests of one position are issued back to
+// back by the same thread and can only name 3 different rows.  Measured (ncu r1e): this does NOT help — requests to
+// a line whose miss is still in flight are not merged (L2 sectors go up, not down) and the kernel is bound by the L1
+// data pipe (82 % busy at G = 1: 15.5 MB of key rows per ciphertext at 128 B/clk), so G = 1 is the default and the
+// other values remain as tuning options.
 constexpr int kKsThreads = 160;
 
-template <int T, int BASEBIT>
+template <int T, int BASEBIT, int G>
 __global__ void __launch_bounds__(kKsThreads)
     keyswitch_kernel(const int32_t* __restrict__ ksk, int n, int64_t stride, const int32_t* __restrict__ u,
-                     const KsJob* __restrict__ jobs, int32_t* __restrict__ pool) {
+                     const KsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ pool) {
     constexpr int BASE = 1 << BASEBIT;
     constexpr uint32_t PREC_OFFSET = 1u << (32 - (1 + BASEBIT * T));
-    __shared__ uint32_t abar[kN];
-    const KsJob job = jobs[blockIdx.x];
-    const int32_t* u0 = u + (int64_t)job.u0 * kUStride;
-    const int32_t* u1 = job.u1 >= 0 ? u + (int64_t)job.u1 * kUStride : nullptr;
-    for (int i = threadIdx.x; i < kN; i += blockDim.x) {
-        uint32_t a = (uint32_t)u0[i];
-        if (u1) a += (uint32_t)u1[i];
-        abar[i] = a + PREC_OFFSET;
+    __shared__ uint32_t abar[kN][G];  // [i][g]: the G words of one coefficient are one broadcast load
+    const int t = threadIdx.x;
+    const int64_t g0 = (int64_t)blockIdx.x * G;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g0 + g < count) {
+            const KsJob job = jobs[g0 + g];
+            const int32_t* u0 = u + (int64_t)job.u0 * kUStride;
+            const int32_t* u1 = job.u1 >= 0 ? u + (int64_t)job.u1 * kUStride : nullptr;
+            for (int i = t; i < kN; i += kKsThreads) {
+                uint32_t a = (uint32_t)u0[i];
+                if (u1) a += (uint32_t)u1[i];
+                abar[i][g] = a + PREC_OFFSET;
+            }
+        } else {
+            for (int i = t; i < kN; i += kKsThreads) abar[i][g] = 0;  // all digits 0: nothing is fetched
+        }
     }
     __syncthreads();
-    const int w0 = 4 * threadIdx.x;
+    const int w0 = 4 * t;
     if (w0 > n) return;
-    uint4 acc = make_uint4(0, 0, 0, 0);
-    const uint4* base = reinterpret_cast<const uint4*>(ksk) + threadIdx.x;
-    const int64_t row4 = stride / 4;
+    uint4 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = make_uint4(0, 0, 0, 0);
+    // address of a row = p0 + (i*T*(BASE-1) + j*(BASE-1) + d-1) * row_bytes: one IADD3 + one IMAD.WIDE.U32 per digit
+    const uint32_t row_bytes = (uint32_t)stride * 4u;
+    uint64_t p0 = reinterpret_cast<uint64_t>(ksk) + 16u * (uint32_t)t;
+    asm volatile("" : "+l"(p0));  // keep the per-thread base in a register pair (ptxas otherwise re-adds it per digit)
+#pragma unroll 1
     for (int i = 0; i < kN; ++i) {
-        const uint32_t a = abar[i];
-        uint4 v[T];
+        uint32_t a[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) a[g] = abar[i][g];
+        const uint32_t ki = (uint32_t)i * (T * (BASE - 1));
 #pragma unroll
         for (int j = 0; j < T; ++j) {
-            const uint32_t d = (a >> (32 - (j + 1) * BASEBIT)) & (BASE - 1);
-            v[j] = make_uint4(0, 0, 0, 0);
-            if (d != 0) v[j] = __ldg(base + (((int64_t)i * T + j) * (BASE - 1) + (d - 1)) * row4);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint32_t d = (a[g] >> (32 - (j + 1) * BASEBIT)) & (BASE - 1);
+                if (d != 0) {
+                    const uint32_t idx = d + ki + (uint32_t)(j * (BASE - 1) - 1);
+                    uint64_t addr;
+                    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(row_bytes), "l"(p0));
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(addr));
+                    acc[g].x -= v.x; acc[g].y -= v.y; acc[g].z -= v.z; acc[g].w -= v.w;
+                }
+            }
         }
-#pragma unroll
-        for (int j = 0; j < T; ++j) { acc.x -= v[j].x; acc.y -= v[j].y; acc.z -= v[j].z; acc.w -= v[j].w; }
     }
-    // b' (+ b'' + c0) goes to word n
-    uint32_t bsum = (uint32_t)u0[kN] + (uint32_t)job.c0;
-    if (u1) bsum += (uint32_t)u1[kN];
-    uint32_t r[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (w0 + q == n) r[q] += bsum;
-    int32_t* out = pool + job.out_slot * stride;
+    for (int g = 0; g < G; ++g) {
+        if (g0 + g >= count) break;
+        const KsJob job = jobs[g0 + g];
+        // b' (+ b'' + c0) goes to word n
+        uint32_t bsum = (uint32_t)u[(int64_t)job.u0 * kUStride + kN] + (uint32_t)job.c0;
+        if (job.u1 >= 0) bsum += (uint32_t)u[(int64_t)job.u1 * kUStride + kN];
+        uint32_t r[4] = {acc[g].x, acc[g].y, acc[g].z, acc[g].w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-        if (w0 + q <= n) out[w0 + q] = (int32_t)r[q];
+        for (int q = 0; q < 4; ++q)
+            if (w0 + q == n) r[q] += bsum;
+        int32_t* out = pool + job.out_slot * stride;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (w0 + q <= n) out[w0 + q] = (int32_t)r[q];
+    }
 }
 
 // K4.  out = sign*in + (0, cst); in < 0: absent.
@@ -364,6 +397,7 @@ struct peba1_cuda_ctx {
     size_t h_stage_cap = 0;
     // options
     int teams_per_cta = 6;
+    int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default)
     int64_t max_pbs_per_launch = 1 << 18;
     // stats
@@ -476,7 +510,15 @@ int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const Pbs
 
 int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t count, int32_t* pool) {
     if (count <= 0) return 0;
-    keyswitch_kernel<8, 2><<<(unsigned)count, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, pool);
+    const int G = c->ks_group;
+    const unsigned grid = (unsigned)((count + G - 1) / G);
+    switch (G) {
+        case 2: keyswitch_kernel<8, 2, 2><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
+        case 4: keyswitch_kernel<8, 2, 4><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
+        case 8: keyswitch_kernel<8, 2, 8><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
+        case 6: keyswitch_kernel<8, 2, 6><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
+        default: keyswitch_kernel<8, 2, 1><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
+    }
     CU(cudaGetLastError());
     if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
     c->stats.launches++;
@@ -988,6 +1030,12 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         if (value == 0) value = 6;
         if (value < 1 || value > 6) return fail(PEBA1_EINVAL, "teams_per_cta must be 1..6");
         c->teams_per_cta = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_group")) {
+        if (value == 0) value = 1;
+        if (value != 1 && value != 2 && value != 4 && value != 6 && value != 8) return fail(PEBA1_EINVAL, "ks_group must be 1, 2, 4, 6 or 8");
+        c->ks_group = (int)value;
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
