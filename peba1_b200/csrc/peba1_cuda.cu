@@ -102,6 +102,27 @@ struct DevEnvTm {
     int bar_id;
     int sums_col;
     uint32_t tm_base;  // allocation base + this warp's lane quarter
+    int chunk_id = 0;  // shared-key variant: quarter of each key row this team fetches
+    uint32_t group_mbar = 0;  // shared-key variant: smem address of the group's two mbarriers (one per row buffer)
+    // split-phase group barrier: one arrival per warp (8 warps per group)
+    __device__ __forceinline__ void group_arrive(int buf) const {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0)
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(group_mbar + 8u * (uint32_t)buf) : "memory");
+    }
+    __device__ __forceinline__ void group_wait(int buf, int parity) const {
+        const uint32_t addr = group_mbar + 8u * (uint32_t)buf;
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done) : "r"(addr), "r"((uint32_t)parity) : "memory");
+        } while (!done);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     __device__ __forceinline__ void team_sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTeam) : "memory"); }
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ int32_t ldg(const int32_t* p) const { return __ldg(p); }
@@ -155,8 +176,8 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
 
 // K0+K1, tensor-memory version: 8 teams (512 threads, 16 warps) per CTA, one CTA per SM, <= 128 registers.
 constexpr int kTeamsTm = 8;
-template <int L, int BGBIT>
-__global__ void __launch_bounds__(kTeamsTm* kTeam, 1)
+template <int L, int BGBIT, int TEAMS>
+__global__ void __launch_bounds__(TEAMS* kTeam, 1)
     pbs_kernel_tm(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
                   const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,10 +207,62 @@ __global__ void __launch_bounds__(kTeamsTm* kTeam, 1)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t g = (int64_t)blockIdx.x * kTeamsTm + team;
+    const int64_t g = (int64_t)blockIdx.x * TEAMS + team;
     if (g < count)
         blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
                                        u_out + g * (int64_t)kUStride);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_alloc_base));
+}
+
+// K0+K1, shared-key tensor-memory version (blind_rotate_team_tmsh): as pbs_kernel_tm, plus the even teams and the odd
+// teams each form a group that fetches every key row once and shares it through tensor memory.
+template <int L, int BGBIT>
+__global__ void __launch_bounds__(kTeamsTm* kTeam, 1)
+    pbs_kernel_tmsh(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
+                    const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TeamSmemTm* teams = reinterpret_cast<TeamSmemTm*>(smem_raw);
+    __shared__ uint32_t tm_alloc_base;
+    __shared__ __align__(8) uint64_t group_mbars[2][2];  // [group][row buffer]
+    const int warp = threadIdx.x >> 5;
+    const int team = threadIdx.x / kTeam;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"l"(
+            (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (threadIdx.x == 32) {
+        for (int q = 0; q < 4; ++q)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(
+                (uint32_t)__cvta_generic_to_shared(&group_mbars[q >> 1][q & 1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 64 * (warp >> 2),
+                 tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16), team >> 1,
+                 (uint32_t)__cvta_generic_to_shared(&group_mbars[team & 1][0])};
+    if ((warp >> 2) == 0) {
+        TeamTwiddles tw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            tw.tw1[j] = c_tables.tw1[env.tid][j];
+            tw.tw2[j] = c_tables.tw2[env.tid & 7][j];
+        }
+        tm_store_twiddles(env, tw);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int64_t g = (int64_t)blockIdx.x * kTeamsTm + team;
+    const bool live = g < count;
+    if (!live) g = count - 1;  // a team without a job shadows the last one: it must still feed its group
+    blind_rotate_team_tmsh<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g], live,
+                                     u_out + g * (int64_t)kUStride);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -397,6 +470,7 @@ struct peba1_cuda_ctx {
     size_t h_stage_cap = 0;
     // options
     int teams_per_cta = 6;
+    int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default)
     int64_t max_pbs_per_launch = 1 << 18;
@@ -464,19 +538,46 @@ int launch_pbs_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const P
     return 0;
 }
 
+template <int L, int BGBIT, int TEAMS>
+int launch_pbs_tm_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
+                    int32_t* u) {
+    const size_t smem = sizeof(TeamSmemTm) * (size_t)TEAMS;
+    const unsigned grid = (unsigned)((count + TEAMS - 1) / TEAMS);
+    auto k = pbs_kernel_tm<L, BGBIT, TEAMS>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, TEAMS * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+    return 0;
+}
+
+template <int L, int BGBIT>
+int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
+                    int32_t* u) {
+    if (c->kernel_variant == 2) {
+        const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
+        const unsigned grid = (unsigned)((count + kTeamsTm - 1) / kTeamsTm);
+        auto k = pbs_kernel_tmsh<L, BGBIT>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+        return 0;
+    }
+    // Narrow levels (the long tail of a circuit: tens of gates per launch) cannot fill 148 SMs with 8 bootstraps per
+    // CTA; fewer teams per CTA spread them over more SMs, where a team runs faster alone.
+    int teams = c->tm_teams;
+    if (teams == 0) teams = count >= (int64_t)c->sm_count * 8 ? 8 : count >= (int64_t)c->sm_count * 4 ? 4
+                          : count >= (int64_t)c->sm_count * 2 ? 2 : 1;
+    switch (teams) {
+        case 1: return launch_pbs_tm_t<L, BGBIT, 1>(c, pool, stride, jobs, count, u);
+        case 2: return launch_pbs_tm_t<L, BGBIT, 2>(c, pool, stride, jobs, count, u);
+        case 4: return launch_pbs_tm_t<L, BGBIT, 4>(c, pool, stride, jobs, count, u);
+        default: return launch_pbs_tm_t<L, BGBIT, 8>(c, pool, stride, jobs, count, u);
+    }
+}
+
 int launch_pbs_tm(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
                   int32_t* u) {
-    const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
-    const unsigned grid = (unsigned)((count + kTeamsTm - 1) / kTeamsTm);
-    if (c->p.l == 3) {
-        auto k = pbs_kernel_tm<3, 7>;
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
-    } else {
-        auto k = pbs_kernel_tm<2, 10>;
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
-    }
+    int rc = c->p.l == 3 ? launch_pbs_tm_l<3, 7>(c, pool, stride, jobs, count, u)
+                         : launch_pbs_tm_l<2, 10>(c, pool, stride, jobs, count, u);
+    if (rc) return rc;
     CU(cudaGetLastError());
     c->stats.launches++;
     return 0;
@@ -487,7 +588,7 @@ int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const Pbs
     if (count <= 0) return 0;
     if (c->timing) CU(cudaEventRecord(c->ev0, c->stream));
     int rc;
-    if (c->kernel_variant == 1) {
+    if (c->kernel_variant >= 1) {
         rc = launch_pbs_tm(c, pool, stride, jobs, count, u);
         if (rc) return rc;
         if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
@@ -606,7 +707,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
-    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) == 0 ? 0 : 1;  // tuning aid
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 2 ? atoi(v) : 1;  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
@@ -1032,6 +1133,11 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         c->teams_per_cta = (int)value;
         return 0;
     }
+    if (!strcmp(name, "tm_teams")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(PEBA1_EINVAL, "tm_teams must be 0, 1, 2, 4 or 8");
+        c->tm_teams = (int)value;
+        return 0;
+    }
     if (!strcmp(name, "ks_group")) {
         if (value == 0) value = 1;
         if (value != 1 && value != 2 && value != 4 && value != 6 && value != 8) return fail(PEBA1_EINVAL, "ks_group must be 1, 2, 4, 6 or 8");
@@ -1039,7 +1145,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value != 0 && value != 1) return fail(PEBA1_EINVAL, "kernel_variant must be 0 or 1");
+        if (value < 0 || value > 2) return fail(PEBA1_EINVAL, "kernel_variant must be 0, 1 or 2");
         c->kernel_variant = (int)value;
         return 0;
     }

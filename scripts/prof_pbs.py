@@ -15,8 +15,8 @@ cts = rng.integers(-2**31, 2**31, size=(2*n, 631), dtype=np.int64).astype(np.int
 eng.reserve(3*n); eng.upload(0, cts)
 eng.enable_timing(True)
 eng.set_option("teams_per_cta", teams if teams <= 6 else 6)
-if teams == 8:
-    eng.set_option("kernel_variant", 1)
+if teams >= 8:
+    eng.set_option("kernel_variant", 1 if teams == 8 else 2)
 g = make_gates("NAND", np.arange(n), n+np.arange(n), 2*n+np.arange(n))
 for rep in range(3):
     eng.gates(g)
