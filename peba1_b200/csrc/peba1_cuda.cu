@@ -299,8 +299,9 @@ constexpr int kKsThreads = 160;
 
 template <int T, int BASEBIT, int G>
 __global__ void __launch_bounds__(kKsThreads)
-    keyswitch_kernel(const int32_t* __restrict__ ksk, int n, int64_t stride, const int32_t* __restrict__ u,
-                     const KsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ pool) {
+    keyswitch_kernel(const int32_t* __restrict__ ksk, int n, int64_t kstride, int64_t stride,
+                     const int32_t* __restrict__ u, const KsJob* __restrict__ jobs, int64_t count,
+                     int32_t* __restrict__ pool) {
     constexpr int BASE = 1 << BASEBIT;
     constexpr uint32_t PREC_OFFSET = 1u << (32 - (1 + BASEBIT * T));
     __shared__ uint32_t abar[kN][G];  // [i][g]: the G words of one coefficient are one broadcast load
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(kKsThreads)
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = make_uint4(0, 0, 0, 0);
     // address of a row = p0 + (i*T*(BASE-1) + j*(BASE-1) + d-1) * row_bytes: one IADD3 + one IMAD.WIDE.U32 per digit
-    const uint32_t row_bytes = (uint32_t)stride * 4u;
+    const uint32_t row_bytes = (uint32_t)kstride * 4u;  // key rows are padded to 128-byte lines (see ksk_stride)
     uint64_t p0 = reinterpret_cast<uint64_t>(ksk) + 16u * (uint32_t)t;
     asm volatile("" : "+l"(p0));  // keep the per-thread base in a register pair (ptxas otherwise re-adds it per digit)
 #pragma unroll 1
@@ -457,6 +458,7 @@ struct peba1_cuda_ctx {
     // pool
     int32_t* pool = nullptr;
     int64_t pool_slots = 0, pool_stride = 0;
+    int64_t ksk_stride = 0;  // words per packed keyswitch-key row
     // workspaces (grown on demand)
     int32_t* u = nullptr;
     int64_t u_cap = 0;  // in samples
@@ -614,11 +616,11 @@ int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t co
     const int G = c->ks_group;
     const unsigned grid = (unsigned)((count + G - 1) / G);
     switch (G) {
-        case 2: keyswitch_kernel<8, 2, 2><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
-        case 4: keyswitch_kernel<8, 2, 4><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
-        case 8: keyswitch_kernel<8, 2, 8><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
-        case 6: keyswitch_kernel<8, 2, 6><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
-        default: keyswitch_kernel<8, 2, 1><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->pool_stride, u, jobs, count, pool); break;
+        case 2: keyswitch_kernel<8, 2, 2><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
+        case 4: keyswitch_kernel<8, 2, 4><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
+        case 8: keyswitch_kernel<8, 2, 8><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
+        case 6: keyswitch_kernel<8, 2, 6><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
+        default: keyswitch_kernel<8, 2, 1><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
     }
     CU(cudaGetLastError());
     if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
@@ -717,7 +719,9 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     build_twiddle_tables(tables);
     CU(cudaMemcpyToSymbol(c_tables, &tables, sizeof tables));
     c->bkfft_bytes = (size_t)params->n * c->rows * 2 * kM * sizeof(double2);
-    c->ksk_bytes = (size_t)kN * params->ks_t * ((1 << params->ks_basebit) - 1) * c->pool_stride * sizeof(int32_t);
+    // key rows start on 128-byte lines: a warp's 512-byte segment then covers 4 lines instead of straddling 5
+    c->ksk_stride = ((int64_t)params->n + 1 + 31) / 32 * 32;
+    c->ksk_bytes = (size_t)kN * params->ks_t * ((1 << params->ks_basebit) - 1) * c->ksk_stride * sizeof(int32_t);
     CU(cudaMalloc(&c->bkfft, c->bkfft_bytes));
     CU(cudaMalloc(&c->ksk, c->ksk_bytes));
     *out = c;
@@ -777,7 +781,7 @@ int peba1_cuda_load_keyswitch_key(peba1_cuda_ctx* c, const int32_t* ksk_host) {
     CU(cudaMalloc(&d_src, words * sizeof(int32_t)));
     CU(cudaMemcpyAsync(d_src, ksk_host, words * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     const int64_t rows_out = (int64_t)kN * c->p.ks_t * (base - 1);
-    ksk_pack_kernel<<<(unsigned)rows_out, 128, 0, c->stream>>>(d_src, c->p.n, base, c->pool_stride, rows_out, c->ksk);
+    ksk_pack_kernel<<<(unsigned)rows_out, 128, 0, c->stream>>>(d_src, c->p.n, base, c->ksk_stride, rows_out, c->ksk);
     CU(cudaGetLastError());
     c->stats.launches++;
     CU(cudaStreamSynchronize(c->stream));
