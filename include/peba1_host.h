@@ -37,6 +37,14 @@ void peba1_batch_end(void); /* closes the batch and flushes when the outermost o
 /* eager = 1 (default): the outermost Math.h routine flushes before returning, which keeps the reference's per-routine
    wall-clock timings (src/main.cpp:310-312) meaningful.  eager = 0: flush only on decrypt / peba1_flush. */
 void peba1_set_eager(int eager);
+/* Circuit mode.  0 = FAITHFUL (default): every gate the reference issues is bootstrapped, also
+   on trivial inputs (quirk Q6) and when its result is never used, so raw ciphertexts equal a per-gate evaluation.
+   1 = FOLD: gates with constant, repeated or complementary operands become constants / aliases / cheaper gates at
+   record time, and gates nobody consumes are dropped at flush.  2 = FOLD + the full adder's carry as one MUX
+   (2 bootstraps + 1 keyswitch) instead of 3 AND + 2 XOR.  Modes 1 and 2 keep every DECRYPTED result; raw ciphertexts
+   differ.  Changing the mode flushes first. */
+void peba1_set_mode(int mode);
+int peba1_get_mode(void);
 
 typedef struct {
     uint64_t gates;        /* bootstrapped gates recorded (MUX counts once) */
@@ -48,6 +56,9 @@ typedef struct {
     uint64_t uploads, downloads; /* ciphertexts moved host->device / device->host */
     uint64_t live_slots, peak_slots;
     double flush_seconds;  /* wall time spent inside flushes */
+    uint64_t executed_gates, executed_pbs; /* what was actually launched (differs from gates/pbs in fold mode) */
+    uint64_t folded;       /* gates replaced by a constant, an alias or a cheaper gate at record time (fold mode) */
+    uint64_t dead;         /* recorded gates dropped at flush because nothing consumed them (fold mode) */
 } peba1_host_stats;
 void peba1_get_stats(peba1_host_stats* out);
 void peba1_reset_stats(void);

@@ -74,6 +74,12 @@ struct Builder {
     // reference bootsADD1bit (Math.cpp:27-50): sum = (a^b)^c ; c' = ((a&b) ^ (a&c)) ^ (c&b) — 4 XOR + 3 AND
     Bit full_adder(const Bit& a, const Bit& b, Bit& carry) const {
         const Bit c0 = carry;
+        if (recorder_mode() >= 2) {  // optimised adder: carry' = (a == b) ? a : carry — one MUX on the shared a^b
+            const Bit t = XOR(a, b);
+            Bit sum2 = XOR(t, c0);
+            carry = MUX(t, c0, a);
+            return sum2;
+        }
         Bit sum = XOR(XOR(a, b), c0);
         const Bit ab = AND(a, b);
         const Bit ac = AND(a, c0);

@@ -51,6 +51,7 @@ struct RoutineScope {
 Handle sample_handle(Engine* e, const LweSample* s);  // borrowed (the sample keeps its reference); uploads host values
 void sample_assign(LweSample* s, Handle h);           // the sample takes over one reference the caller owns
 
+int recorder_mode();  // peba1_set_mode
 void note_linear();  // statistics: a NOT/COPY/CONSTANT that cost nothing
 
 }  // namespace peba1

@@ -77,6 +77,7 @@ static int g_batch_depth = 0;
 static bool g_eager = true;
 static peba1_host_stats g_stats{};
 static const peba1_test_backend* g_test_backend = nullptr;
+static int g_mode = 0;  // peba1_set_mode: 0 faithful, 1 fold + dead-gate elimination, 2 = 1 + MUX-carry adders
 
 // The four engine operations the recorder needs.  The product path is libpeba1_cuda; the table exists only so the
 // CPU test-suite can observe the schedule (tests/ installs a bit-level simulator).
@@ -223,8 +224,23 @@ static Handle push_node(Engine* e, peba1_gate& g, int level) {
     return (Handle)out << 1;
 }
 
-Handle record_gate(Engine* e, int op, Handle a, Handle b) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+// Boolean function of a 2-input gate (SURVEY.md §8a constants)
+static inline int eval2(int op, int x, int y) {
+    switch (op) {
+        case PEBA1_OP_NAND: return 1 - (x & y);
+        case PEBA1_OP_AND: return x & y;
+        case PEBA1_OP_OR: return x | y;
+        case PEBA1_OP_XOR: return x ^ y;
+        case PEBA1_OP_XNOR: return 1 - (x ^ y);
+        case PEBA1_OP_NOR: return 1 - (x | y);
+        case PEBA1_OP_ANDNY: return (1 - x) & y;
+        case PEBA1_OP_ANDYN: return x & (1 - y);
+        case PEBA1_OP_ORNY: return (1 - x) | y;
+        default: return x | (1 - y);  // ORYN
+    }
+}
+
+static Handle record_gate_raw(Engine* e, int op, Handle a, Handle b) {
     peba1_gate g{};
     g.op = op;
     const int la = set_operand(g, 0, a), lb = set_operand(g, 1, b);
@@ -233,8 +249,89 @@ Handle record_gate(Engine* e, int op, Handle a, Handle b) {
     return push_node(e, g, 1 + std::max(la, lb));
 }
 
+// Fold mode (changes raw ciphertexts, never decrypted results): a gate or MUX whose operands
+// involve fewer distinct variables than its arity is replaced by a constant, an alias (possibly negated: free), or a
+// cheaper 2-input gate.  Operands are (variable wire, polarity) or constants.
+struct FoldOperand { int64_t var; int neg; int cst; };  // var < 0: constant cst
+static inline FoldOperand fold_operand(Handle h) {
+    if (is_const(h)) return FoldOperand{-1, 0, (int)(h & 1)};
+    return FoldOperand{(int64_t)(h >> 1), (int)(h & 1), 0};
+}
+static inline int fold_value(const FoldOperand& o, const int64_t* vars, const int* vals, int nvars) {
+    if (o.var < 0) return o.cst;
+    for (int q = 0; q < nvars; ++q)
+        if (vars[q] == o.var) return vals[q] ^ o.neg;
+    return 0;
+}
+// returns true and sets *out (one reference owned by the caller) when `nin` operands under `fn` reduce
+template <class Fn>
+static bool try_fold(Engine* e, const Handle* in, int nin, Fn fn, Handle* out) {
+    FoldOperand o[3];
+    int64_t vars[3];
+    int nvars = 0;
+    for (int q = 0; q < nin; ++q) {
+        o[q] = fold_operand(in[q]);
+        if (o[q].var < 0) continue;
+        bool seen = false;
+        for (int k = 0; k < nvars; ++k) seen |= vars[k] == o[q].var;
+        if (!seen) vars[nvars++] = o[q].var;
+    }
+    if (nvars >= nin) return false;  // nothing to fold
+    int table[4] = {0, 0, 0, 0};
+    const int rows = 1 << nvars;
+    for (int m = 0; m < rows; ++m) {
+        const int vals[3] = {m & 1, (m >> 1) & 1, 0};
+        int v[3];
+        for (int q = 0; q < nin; ++q) v[q] = fold_value(o[q], vars, vals, nvars);
+        table[m] = fn(v);
+    }
+    auto alias = [&](int64_t var, int neg) {
+        const Handle h = ((Handle)var << 1) | (Handle)neg;
+        retain(h);
+        *out = h;
+    };
+    if (nvars == 0) { *out = table[0] ? kTrue : kFalse; g_stats.folded++; return true; }
+    if (nvars == 1) {
+        if (table[0] == table[1]) *out = table[0] ? kTrue : kFalse;
+        else alias(vars[0], table[0]);  // table = {0,1}: x ; {1,0}: NOT x
+        g_stats.folded++;
+        return true;
+    }
+    // two variables x = vars[0] (bit 0 of m), y = vars[1] (bit 1 of m)
+    const bool dep_x = table[0] != table[1] || table[2] != table[3];
+    const bool dep_y = table[0] != table[2] || table[1] != table[3];
+    if (!dep_x && !dep_y) { *out = table[0] ? kTrue : kFalse; g_stats.folded++; return true; }
+    if (!dep_y) { alias(vars[0], table[0]); g_stats.folded++; return true; }
+    if (!dep_x) { alias(vars[1], table[0]); g_stats.folded++; return true; }
+    for (int op = PEBA1_OP_NAND; op <= PEBA1_OP_ORYN; ++op) {
+        bool ok = true;
+        for (int m = 0; m < 4 && ok; ++m) ok = eval2(op, m & 1, (m >> 1) & 1) == table[m];
+        if (ok) {
+            *out = record_gate_raw(e, op, (Handle)vars[0] << 1, (Handle)vars[1] << 1);
+            g_stats.folded++;
+            return true;
+        }
+    }
+    return false;  // unreachable: the ten gate types cover every 2-variable function that depends on both
+}
+
+Handle record_gate(Engine* e, int op, Handle a, Handle b) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_mode >= 1) {
+        const Handle in[2] = {a, b};
+        Handle out;
+        if (try_fold(e, in, 2, [op](const int* v) { return eval2(op, v[0], v[1]); }, &out)) return out;
+    }
+    return record_gate_raw(e, op, a, b);
+}
+
 Handle record_mux(Engine* e, Handle sel, Handle if1, Handle if0) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (g_mode >= 1) {
+        const Handle in[3] = {sel, if1, if0};
+        Handle out;
+        if (try_fold(e, in, 3, [](const int* v) { return v[0] ? v[1] : v[2]; }, &out)) return out;
+    }
     peba1_gate g{};
     g.op = PEBA1_OP_MUX;
     const int l0 = set_operand(g, 0, sel), l1 = set_operand(g, 1, if1), l2 = set_operand(g, 2, if0);
@@ -242,6 +339,8 @@ Handle record_mux(Engine* e, Handle sel, Handle if1, Handle if0) {
     g_stats.pbs += 2;
     return push_node(e, g, 1 + std::max(l0, std::max(l1, l2)));
 }
+
+int recorder_mode() { return g_mode; }
 
 Handle wire_from_host(Engine* e, const int32_t* words) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -267,12 +366,36 @@ void flush(Engine* e) {
         e->up_wires.clear();
         e->up_words.clear();
     }
+    // 1b. fold mode: dead-gate elimination.  A pending node whose output is referenced by nobody but itself (no
+    // sample, no builder temporary, no live consumer) is dropped; walking the levels from the last to the first lets
+    // the release of its operands cascade.
+    if (g_mode >= 1) {
+        for (size_t lv = e->levels.size(); lv-- > 0;) {
+            auto& nodes = e->levels[lv];
+            size_t keep = 0;
+            for (size_t i = 0; i < nodes.size(); ++i) {
+                const peba1_gate nd = nodes[i];
+                if (g_wires[nd.out].refs == 1) {
+                    const int nin = nd.op == PEBA1_OP_MUX ? 3 : 2;
+                    for (int q = 0; q < nin; ++q)
+                        if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(nd.in[q]);
+                    unref_wire(nd.out);
+                    g_stats.dead++;
+                } else {
+                    nodes[keep++] = nd;
+                }
+            }
+            nodes.resize(keep);
+        }
+    }
     // 2. one batched launch pair per level
     for (auto& nodes : e->levels) {
         if (nodes.empty()) continue;
         e->scratch.resize(nodes.size());
         for (size_t i = 0; i < nodes.size(); ++i) {
             const peba1_gate& nd = nodes[i];
+            g_stats.executed_gates++;
+            g_stats.executed_pbs += nd.op == PEBA1_OP_MUX ? 2 : 1;
             peba1_gate& g = e->scratch[i];
             g = nd;
             const int nin = nd.op == PEBA1_OP_MUX ? 3 : 2;
@@ -638,6 +761,12 @@ void peba1_batch_end(void) {
     if (g_batch_depth > 0 && --g_batch_depth == 0) peba1_flush();
 }
 void peba1_set_eager(int eager) { g_eager = eager != 0; }
+void peba1_set_mode(int mode) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    for (Engine* e : g_engines) flush(e);  // pending work was recorded under the old mode
+    g_mode = mode < 0 ? 0 : mode > 2 ? 2 : mode;
+}
+int peba1_get_mode(void) { return g_mode; }
 void peba1_get_stats(peba1_host_stats* out) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (out) *out = g_stats;

@@ -37,7 +37,8 @@ class HostStats(C.Structure):
     _fields_ = [("gates", C.c_uint64), ("pbs", C.c_uint64), ("linear", C.c_uint64), ("levels", C.c_uint64),
                 ("flushes", C.c_uint64), ("max_level_width", C.c_uint64), ("uploads", C.c_uint64),
                 ("downloads", C.c_uint64), ("live_slots", C.c_uint64), ("peak_slots", C.c_uint64),
-                ("flush_seconds", C.c_double)]
+                ("flush_seconds", C.c_double), ("executed_gates", C.c_uint64), ("executed_pbs", C.c_uint64),
+                ("folded", C.c_uint64), ("dead", C.c_uint64)]
 
 
 class TestBackend(C.Structure):
@@ -92,6 +93,8 @@ def load_library():
     L.peba1_host_set_device.argtypes = [C.c_int]
     L.peba1_host_set_test_backend.argtypes = [C.POINTER(TestBackend)]
     L.peba1_set_eager.argtypes = [C.c_int]
+    L.peba1_set_mode.argtypes = [C.c_int]
+    L.peba1_get_mode.restype = C.c_int
     L.peba1_get_stats.argtypes = [C.POINTER(HostStats)]
     L.peba1_sample_get.argtypes = [LS, CK, i32p]
     L.peba1_sample_set.argtypes = [LS, i32p]

@@ -272,3 +272,74 @@ def test_slots_are_recycled(env):
     """after everything above was freed the pool holds (almost) nothing live"""
     L, ks, sim = env
     assert ks.stats().live_slots < 64
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fold_modes_keep_decrypted_results(env, mode):
+    """constant folding + dead-gate elimination (mode 1) and MUX-carry adders (mode 2) change the
+    number of bootstraps, never a decrypted result — including the reference's quirks (Q1, Q3)."""
+    L, ks, sim = env
+    L.peba1_set_mode(mode)
+    try:
+        rng = np.random.default_rng(40 + mode)
+        for x, y in [(200, 13), (13, 200), (77, 0), (255, 255)] + [tuple(int(v) for v in rng.integers(0, 256, 2)) for _ in range(4)]:
+            a, b = ks.encrypt_int(x, 8, 50), ks.encrypt_int(y, 8, 51)
+            r, c, d, m = ks.new_array(8), ks.new_array(1), ks.new_array(9), ks.new_array(23)
+            s0 = ks.stats()
+            L.peba1_batch_begin()
+            L.peba1_math_add(r, a, b, c, 8, ks.cloud)
+            L.peba1_math_sub(d, a, b, 8, ks.cloud)
+            L.peba1_math_multiply(m, a, b, 8, 0, ks.cloud)
+            L.peba1_batch_end()
+            s1 = ks.stats()
+            assert ks.decrypt_int(r, 8) == (x + y) % 256 and ks.decrypt_int(c, 1) == (x + y) >> 8
+            assert ks.decrypt_int(d, 9) == ref_sub(x, y)
+            assert ks.decrypt_int(m, 23) == x * y
+            assert s1.executed_pbs - s0.executed_pbs < (56 + 226 + 1296) * 0.62      # at least 38 % fewer bootstraps
+            for arr, n in ((a, 8), (b, 8), (r, 8), (c, 1), (d, 9), (m, 23)):
+                ks.free_array(n, arr)
+        # protocol path on 4 slots
+        t = np.array([10, 20, 30, 40])
+        for probe, bound, expect in [(t + 1, 0, 1), (t + 1, 4, 0), (t + 3, 35, 1), (t + 3, 36, 0)]:
+            ta, tp = _vec(ks, t, 3000)
+            pa, pp = _vec(ks, probe, 4000)
+            eb = ks.encrypt_int(bound, 24, 5000)
+            rb = ks.new_array(24)
+            L.peba1_math_function_f(rb, pp, tp, 4, eb, 8, ks.cloud)
+            assert ks.decrypt_int(rb, 24) == expect
+            e0, e1 = ks.encrypt_int(0x5A, 8, 6000), ks.encrypt_int(0xC3, 8, 6001)
+            y = ks.new_array(9)
+            L.peba1_math_function_g(y, rb, e0, e1, 8, ks.cloud)
+            assert ks.decrypt_int(y, 8) == (0xC3 if expect else (-0x5A) % 256)
+            for arr in ta + pa + [e0, e1]:
+                ks.free_array(8, arr)
+            ks.free_array(24, eb); ks.free_array(24, rb); ks.free_array(9, y)
+    finally:
+        L.peba1_set_mode(0)
+
+
+def test_fold_mode_face_match_size(env):
+    """bootstraps per full-size face match in each mode (reported in DESIGN.md)"""
+    L, ks, sim = env
+    rng = np.random.default_rng(33)
+    t = rng.integers(0, 255, size=128)
+    probe = (t + 1) % 256
+    counts = {}
+    for mode in (0, 1, 2):
+        L.peba1_set_mode(mode)
+        ta, tp = _vec(ks, t, 7000)
+        pa, pp = _vec(ks, probe, 8000)
+        eb = ks.encrypt_int(100, 24, 9000)
+        rb = ks.new_array(24)
+        s0 = ks.stats()
+        sim.reset_schedule()
+        L.peba1_math_function_f(rb, pp, tp, 128, eb, 8, ks.cloud)
+        s1 = ks.stats()
+        counts[mode] = (s1.executed_pbs - s0.executed_pbs, len(sim.level_widths))
+        assert ks.decrypt_int(rb, 24) == 1
+        for arr in ta + pa:
+            ks.free_array(8, arr)
+        ks.free_array(24, eb); ks.free_array(24, rb)
+    L.peba1_set_mode(0)
+    print("PBS and levels per face match by mode:", counts)
+    assert counts[0][0] == 215544 and counts[1][0] < 0.6 * counts[0][0] and counts[2][0] < counts[1][0]

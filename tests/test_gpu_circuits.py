@@ -143,3 +143,36 @@ def test_face_match_function_f_and_g(gpu_keys):
         gpu_keys.free_array(8, e0); gpu_keys.free_array(8, e1)
     for arr in ta + pa:
         gpu_keys.free_array(8, arr)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fold_modes_on_gpu(gpu_keys, mode):
+    """SURVEY.md §8f item 1 on real ciphertexts: fewer bootstraps, identical decrypted results (noise included)."""
+    L = H.load_library()
+    L.peba1_set_mode(mode)
+    try:
+        rng = np.random.default_rng(60 + mode)
+        n = 24
+        xs, ys = rng.integers(0, 256, size=n), rng.integers(0, 256, size=n)
+        ys[0] = 0                                                      # quirk Q1 must survive folding
+        A = [gpu_keys.encrypt_int(int(x), 8, 3000 + i) for i, x in enumerate(xs)]
+        B = [gpu_keys.encrypt_int(int(y), 8, 4000 + i) for i, y in enumerate(ys)]
+        D = [gpu_keys.new_array(9) for _ in range(n)]
+        M = [gpu_keys.new_array(23) for _ in range(n)]
+        s0 = gpu_keys.stats()
+        L.peba1_batch_begin()
+        for i in range(n):
+            L.peba1_math_sub(D[i], A[i], B[i], 8, gpu_keys.cloud)
+            L.peba1_math_multiply(M[i], A[i], B[i], 8, 0, gpu_keys.cloud)
+        L.peba1_batch_end()
+        s1 = gpu_keys.stats()
+        assert s1.executed_pbs - s0.executed_pbs < 0.62 * n * (226 + 1296)
+        for i in range(n):
+            x, y = int(xs[i]), int(ys[i])
+            assert gpu_keys.decrypt_int(D[i], 9) == (abs(x - y) if y else (256 - x) % 512)
+            assert gpu_keys.decrypt_int(M[i], 23) == x * y
+        for i in range(n):
+            gpu_keys.free_array(8, A[i]); gpu_keys.free_array(8, B[i])
+            gpu_keys.free_array(9, D[i]); gpu_keys.free_array(23, M[i])
+    finally:
+        L.peba1_set_mode(0)
