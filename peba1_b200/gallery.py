@@ -34,7 +34,7 @@ def synthetic_gallery(total: int, slots: int = 128, seed: int = 2024, planted: f
     rng = np.random.default_rng(seed)
     probe = rng.integers(1, 256, size=slots)
     gallery = rng.integers(0, 256, size=(total, slots))
-    mask = rng.random(total) < planted
+    mask = (np.arange(total) % max(1, int(round(1 / planted)))) == 1 if planted > 0 else np.zeros(total, bool)
     gallery[mask] = np.clip(probe + rng.integers(-2, 3, size=(int(mask.sum()), slots)), 0, 255)
     dist2 = ((gallery.astype(np.int64) - probe) ** 2).sum(axis=1)
     return probe, gallery, (dist2 > bound).astype(np.int64)
