@@ -210,6 +210,9 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                   # the version banner goes to stdout otherwise
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
