@@ -138,3 +138,51 @@ def test_size_independent_properties_full_batch(engine, keys):
     assert np.all(np.abs(np.abs(ph) - 0.125) < 2.0**-5)
     # determinism: the same launch twice gives identical words
     assert np.array_equal(z, engine.gate_batch_host("XOR", cx, cy))
+
+
+def test_lambda80_parameter_set(oracle):
+    """The second upstream parameter set (minimum_lambda <= 80: n=500, l=2, Bgbit=10) through the same kernels."""
+    import peba1_b200 as P
+    K = oracle.Keys.generate(oracle.default_params(80), 7)
+    eng = P.Engine(P.default_params(80), device=0)
+    eng.load_keys(K.bk, K.ksk)
+    rng = np.random.default_rng(8)
+    n = 37
+    a, b, c = (rng.integers(0, 2, size=n) for _ in range(3))
+    ca, cb, cc = K.encrypt(a, 1), K.encrypt(b, 2), K.encrypt(c, 3)
+    for op in ("NAND", "XOR"):
+        got = eng.gate_batch_host(op, ca, cb)
+        assert np.array_equal(got, K.gate_batch(op, ca, cb, threads=os.cpu_count() or 1)), op
+    got = eng.gate_batch_host("MUX", ca, cb, cc)
+    assert np.array_equal(got, K.gate_batch("MUX", ca, cb, cc, threads=os.cpu_count() or 1))
+    assert np.array_equal(K.decrypt(got), np.where(a == 1, b, c))
+    for variant in (0, 2):            # the register kernel and the shared-key kernel give the same words
+        eng.set_option("kernel_variant", variant)
+        assert np.array_equal(eng.gate_batch_host("MUX", ca, cb, cc), got)
+    eng.close()
+    K.close()
+
+
+def test_kernel_variants_agree(engine, keys):
+    """register accumulators (0), tensor-memory accumulators (1, default), shared-key (2): identical words; also the
+    1/2/4/8 teams-per-CTA shapes the launcher picks for narrow levels."""
+    rng = np.random.default_rng(77)
+    n = 45
+    a, b = rng.integers(0, 2, size=n), rng.integers(0, 2, size=n)
+    ca, cb = keys.encrypt(a, 91), keys.encrypt(b, 92)
+    want = keys.gate_batch("ANDYN", ca, cb, threads=os.cpu_count() or 1)
+    try:
+        for variant in (0, 1, 2):
+            engine.set_option("kernel_variant", variant)
+            assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), variant
+        engine.set_option("kernel_variant", 1)
+        for teams in (1, 2, 4, 8):
+            engine.set_option("tm_teams", teams)
+            assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), teams
+        for grp in (2, 4, 6, 8):
+            engine.set_option("ks_group", grp)
+            assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), grp
+    finally:
+        engine.set_option("kernel_variant", 1)
+        engine.set_option("tm_teams", 0)
+        engine.set_option("ks_group", 1)

@@ -119,3 +119,15 @@ def test_output_phase_noise_margin(oracle, keys):
     assert keys.decrypt(out).tolist() == [1 - (int(a) & int(b)) for a, b in zip(bits_a, bits_b)]
     ph = keys.phase(out).astype(np.float64) / 2.0**32
     assert np.all(np.abs(np.abs(ph) - 0.125) < 2.0**-5)
+
+
+def test_lambda80_parameter_set_fft_equals_exact(oracle):
+    """upstream's 80-bit set (n=500, l=2, Bgbit=10): larger digits, still exact after rounding on these samples"""
+    K = oracle.Keys.generate(oracle.default_params(80), 7)
+    a, b = np.array([0, 1, 0, 1]), np.array([0, 0, 1, 1])
+    ca, cb = K.encrypt(a, 1), K.encrypt(b, 2)
+    f = K.gate_batch("NAND", ca, cb, mode=oracle.FFT, threads=4)
+    assert K.decrypt(f).tolist() == (1 - (a & b)).tolist()
+    for i in (0, 3):
+        assert np.array_equal(K.gate("NAND", ca[i], cb[i], mode=oracle.EXACT), f[i])
+    K.close()
