@@ -35,6 +35,8 @@ struct __align__(16) TeamSmemTm {
     double2  ex2[kM];
     int32_t  acc[2][kN];
     uint16_t bara[640];
+    unsigned long long ex1_free;  // mbarrier: "the cross-team exchange buffer may be overwritten" (2 arrivals, one per warp)
+    unsigned long long pad_;
 };
 
 PEBA1_HD double2 words_to_c(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -87,7 +89,7 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
     for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
     radix8<false>(x);
     env.tmem_wait_ld();
-    env.team_sync();  // every reader of the previous transform's ex1 is done
+    env.ex1_acquire();  // every reader of the previous transform's ex1 is done (split-phase: they signalled long ago)
 #pragma unroll
     for (int k0 = 0; k0 < 8; ++k0)
         sm.ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
@@ -96,6 +98,7 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
     const int hi = tid >> 3, lo = tid & 7;
 #pragma unroll
     for (int b = 0; b < 8; ++b) x[b] = sm.ex1[64 * hi + 8 * b + lo];
+    env.ex1_release();
     radix8<false>(x);
     env.tmem_wait_ld();
     sm.ex2[64 * hi + lo] = x[0];
@@ -126,7 +129,7 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) x[k1] = sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)];
     radix8<true>(x);
-    env.team_sync();  // previous readers of ex1 are done
+    env.ex1_acquire();  // previous readers of ex1 are done
 #pragma unroll
     for (int b = 0; b < 8; ++b) sm.ex1[64 * hi + 8 * b + lo] = x[b];
     env.team_sync();
@@ -134,6 +137,7 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
 #pragma unroll
     for (int k0 = 0; k0 < 8; ++k0)
         x[k0] = cmul_conj(sm.ex1[64 * k0 + tid], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
+    env.ex1_release();
     radix8<true>(x);
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul_conj(x[a], w32(a));

@@ -31,6 +31,9 @@ struct HostEnv {
     void tmem_st32(int col, const uint32_t (&w)[32]) const { memcpy(tm + col, w, sizeof w); }
     void tmem_wait_ld() const {}
     void tmem_wait_st() const {}
+    // split-phase "exchange buffer free" barrier of the device code: a full team barrier is a valid (stronger) stand-in
+    void ex1_acquire() { pthread_barrier_wait(team); }
+    void ex1_release() {}
 };
 
 struct Shared {

@@ -104,6 +104,26 @@ struct DevEnvTm {
     uint32_t tm_base;  // allocation base + this warp's lane quarter
     int chunk_id = 0;  // shared-key variant: quarter of each key row this team fetches
     uint32_t group_mbar = 0;  // shared-key variant: smem address of the group's two mbarriers (one per row buffer)
+    uint32_t ex1_mbar = 0;    // smem address of the team's "exchange buffer free" mbarrier
+    uint32_t ex1_phase = 1;   // parity to wait for: the buffer starts free (the phase before the first counts as done)
+    // Split-phase write-after-read protection of the cross-team exchange buffer: a warp signals as soon as its reads
+    // are done, the next writer waits just before writing, one whole transform pass later, so nobody actually blocks.
+    __device__ __forceinline__ void ex1_release() const {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0)
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(ex1_mbar) : "memory");
+    }
+    __device__ __forceinline__ void ex1_acquire() {
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done) : "r"(ex1_mbar), "r"(ex1_phase) : "memory");
+        } while (!done);
+        ex1_phase ^= 1u;
+    }
     // split-phase group barrier: one arrival per warp (8 warps per group)
     __device__ __forceinline__ void group_arrive(int buf) const {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -190,11 +210,16 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
             (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    if ((threadIdx.x % kTeam) == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"((uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 64 * (warp >> 2),
                  tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16)};
+    env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
     if ((warp >> 2) == 0) {  // one warp per lane quarter publishes the per-thread twiddles
         TeamTwiddles tw;
 #pragma unroll
@@ -234,6 +259,8 @@ __global__ void __launch_bounds__(kTeamsTm* kTeam, 1)
             (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    if ((threadIdx.x % kTeam) == 0)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"((uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free)));
     if (threadIdx.x == 32) {
         for (int q = 0; q < 4; ++q)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(
@@ -246,6 +273,7 @@ __global__ void __launch_bounds__(kTeamsTm* kTeam, 1)
     DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 64 * (warp >> 2),
                  tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16), team >> 1,
                  (uint32_t)__cvta_generic_to_shared(&group_mbars[team & 1][0])};
+    env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
     if ((warp >> 2) == 0) {
         TeamTwiddles tw;
 #pragma unroll
