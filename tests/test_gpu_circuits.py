@@ -176,3 +176,55 @@ def test_fold_modes_on_gpu(gpu_keys, mode):
             gpu_keys.free_array(9, D[i]); gpu_keys.free_array(23, M[i])
     finally:
         L.peba1_set_mode(0)
+
+
+def test_config3_adders_4096_instances(gpu_keys):
+    """BASELINE configs[2]: 8- and 16-bit ripple-carry adders, 4,096 instances batched per level (24 / 48 launches pairs);
+    every instance checked against native integer arithmetic (main.cpp:320)."""
+    L = H.load_library()
+    for bits, levels in ((8, 24), (16, 48)):
+        n = 4096
+        rng = np.random.default_rng(bits)
+        xs, ys = rng.integers(0, 1 << bits, size=n), rng.integers(0, 1 << bits, size=n)
+        wa = gpu_keys.encrypt(((xs[:, None] >> np.arange(bits)) & 1).reshape(-1), 11).reshape(n, bits, -1)
+        wb = gpu_keys.encrypt(((ys[:, None] >> np.arange(bits)) & 1).reshape(-1), 12).reshape(n, bits, -1)
+        A, B = [gpu_keys.new_array(bits) for _ in range(n)], [gpu_keys.new_array(bits) for _ in range(n)]
+        R, Cy = [gpu_keys.new_array(bits) for _ in range(n)], [gpu_keys.new_array(1) for _ in range(n)]
+        for i in range(n):
+            gpu_keys.set_words(A[i], wa[i]); gpu_keys.set_words(B[i], wb[i])
+        s0 = gpu_keys.stats()
+        L.peba1_batch_begin()
+        for i in range(n):
+            L.peba1_math_add(R[i], A[i], B[i], Cy[i], bits, gpu_keys.cloud)
+        L.peba1_batch_end()
+        s1 = gpu_keys.stats()
+        assert s1.executed_pbs - s0.executed_pbs == 7 * bits * n and s1.levels - s0.levels == levels
+        out = np.stack([gpu_keys.get_words(R[i], bits) for i in range(n)])
+        got = (gpu_keys.decrypt(out.reshape(n * bits, -1)).reshape(n, bits) << np.arange(bits)).sum(axis=1)
+        assert np.array_equal(got, (xs + ys) % (1 << bits))
+        for i in range(n):
+            for arr, k in ((A[i], bits), (B[i], bits), (R[i], bits), (Cy[i], 1)):
+                gpu_keys.free_array(k, arr)
+
+
+def test_config3_multiplier16_instances(gpu_keys):
+    """BASELINE configs[2]: the 16-bit multiplier (width 47 — the reference's hard-coded 23 parametrised), 64 instances
+    batched per level: 169 launch pairs, 346 k bootstraps."""
+    L = H.load_library()
+    n = 64
+    rng = np.random.default_rng(16)
+    xs, ys = rng.integers(0, 1 << 16, size=n), rng.integers(0, 1 << 16, size=n)
+    A = [gpu_keys.encrypt_int(int(x), 16, 100 + i) for i, x in enumerate(xs)]
+    B = [gpu_keys.encrypt_int(int(y), 16, 900 + i) for i, y in enumerate(ys)]
+    R = [gpu_keys.new_array(47) for _ in range(n)]
+    s0 = gpu_keys.stats()
+    L.peba1_batch_begin()
+    for i in range(n):
+        L.peba1_math_multiply(R[i], A[i], B[i], 16, 47, gpu_keys.cloud)
+    L.peba1_batch_end()
+    s1 = gpu_keys.stats()
+    assert s1.executed_pbs - s0.executed_pbs == 5408 * n and s1.levels - s0.levels == 169
+    for i in range(n):
+        assert gpu_keys.decrypt_int(R[i], 47) == int(xs[i]) * int(ys[i])
+    for i in range(n):
+        gpu_keys.free_array(16, A[i]); gpu_keys.free_array(16, B[i]); gpu_keys.free_array(47, R[i])
