@@ -5,7 +5,7 @@
  * reaches through the TFHE gate API (`bootsAND/OR/XOR/XNOR/MUX/...`, linked from
  * libtfhe-nayuki-portable.so by /root/reference/CMakeLists.txt:10-15 and called at
  * /root/reference/src/Math.cpp:34-43,84,158,165,170,233,260-261,277) is executed here as batched
- * CUDA launches.  The TFHE-compatible host shim (include/tfhe/*.h, peba1_b200/host/) records gates and
+ * CUDA launches.  The TFHE-compatible host shim (the headers under include/tfhe, peba1_b200/host/) records gates and
  * calls these entry points once per circuit level; a foreign-language binding (cgo/JNI/ctypes) would bind
  * exactly these symbols — see INTEGRATION.md.
  *

@@ -34,6 +34,8 @@ typedef struct LweSample {
     Torus32 b;
     double current_variance; /* not tracked by this engine; kept for layout familiarity */
     uint64_t peba1_handle;
+    int32_t peba1_n;         /* number of mask words behind `a` (the parameter set's n) */
+    int32_t peba1_pad;
 } LweSample;
 
 /* Parameter set: upstream's nested LweParams/TGswParams/TLweParams flattened. */

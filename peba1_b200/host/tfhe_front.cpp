@@ -663,6 +663,8 @@ LweSample* new_gate_bootstrapping_ciphertext_array(int32_t nbelems, const TFheGa
         arr[i].b = 0;
         arr[i].current_variance = 0.0;
         arr[i].peba1_handle = kFalse;  // never-written ciphertexts read as trivial false
+        arr[i].peba1_n = params->n;
+        arr[i].peba1_pad = 0;
     }
     return arr;
 }
@@ -795,18 +797,11 @@ void peba1_sample_get(const LweSample* sample, const TFheGateBootstrappingCloudK
     fetch(engine_of(bk), h, words);
 }
 void peba1_sample_set(LweSample* sample, const int32_t* words) {
-    // n is implied by the array allocation; the words pointer layout is a[0..n-1], b
+    // words: a[0..n-1], b
     const Handle old = sample->peba1_handle;
     sample->peba1_handle = 0;
     release(old);
-    // distance between consecutive samples' storage is n words; recover n from the allocation is not possible for a
-    // single sample, so callers pass exactly n+1 words and n comes from the current engine or the first key created.
-    int n = -1;
-    {
-        std::lock_guard<std::recursive_mutex> lk(g_mu);
-        if (g_current) n = g_current->words - 1;
-    }
-    if (n < 0) n = 630;
+    const int n = sample->peba1_n;
     memcpy(sample->a, words, sizeof(int32_t) * (size_t)n);
     sample->b = words[n];
 }

@@ -30,7 +30,7 @@ class SecretKey(C.Structure):
 
 class LweSample(C.Structure):
     _fields_ = [("a", C.POINTER(C.c_int32)), ("b", C.c_int32), ("current_variance", C.c_double),
-                ("peba1_handle", C.c_uint64)]
+                ("peba1_handle", C.c_uint64), ("peba1_n", C.c_int32), ("peba1_pad", C.c_int32)]
 
 
 class HostStats(C.Structure):
