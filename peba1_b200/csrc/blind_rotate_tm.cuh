@@ -101,6 +101,10 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
     env.ex1_release();
     radix8<false>(x);
     env.tmem_wait_ld();
+#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 2  /* what-if build: no inner exchange in the forward transform */
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
+#else
     sm.ex2[64 * hi + lo] = x[0];
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1)
@@ -108,6 +112,7 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
     env.warp_sync();
 #pragma unroll
     for (int c = 0; c < 8; ++c) x[c] = sm.ex2[64 * hi + 8 * lo + (c ^ lo)];
+#endif
     radix8<false>(x);
 }
 
@@ -220,9 +225,14 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, TeamSmemTm& sm, const double2* __re
             double2 b0[4], b1[4];
             const int zsel = r > 0 ? 1 : 0;
 #define PEBA1_CHUNK_COL(q) (zsel ? sums + 32 * ((q) >> 1) + 16 * ((q) & 1) : kTmZero)
+#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 1  /* what-if build (scripts/ablate.sh): no key loads */
+#define PEBA1_CHUNK_LDG(q, b)                                                                              \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e) b[e] = make_double2(1.0 + (q), 0.5 + e);
+#else
 #define PEBA1_CHUNK_LDG(q, b)                                                                              \
     _Pragma("unroll") for (int e = 0; e < 4; ++e)                                                          \
         b[e] = env.ldg2(bk + (size_t)(2 * (4 * ((q) & 1) + e) + ((q) >> 1)) * 64);
+#endif
 #define PEBA1_CHUNK_MAC(q, w, b)                                                                           \
     _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
         double2 sacc = words_to_c(w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                      \

@@ -25,6 +25,8 @@ struct HostEnv {
     // tensor memory of the tensor-memory variant, emulated as a private array of 32-bit cells per thread
     int sums_col = 0;
     uint32_t* tm = nullptr;
+    void tmem_ld8(int col, uint32_t (&w)[8]) const { memcpy(w, tm + col, sizeof w); }
+    void tmem_st8(int col, const uint32_t (&w)[8]) const { memcpy(tm + col, w, sizeof w); }
     void tmem_ld16(int col, uint32_t (&w)[16]) const { memcpy(w, tm + col, sizeof w); }
     void tmem_st16(int col, const uint32_t (&w)[16]) const { memcpy(tm + col, w, sizeof w); }
     void tmem_ld32(int col, uint32_t (&w)[32]) const { memcpy(w, tm + col, sizeof w); }

@@ -61,6 +61,16 @@ struct DevEnv {
 
 // tcgen05 32x32b load/store wrappers (tensor memory used as per-thread scratch; see blind_rotate_tm.cuh)
 #define R8(a, o) "%" #o
+__device__ __forceinline__ void tmem_ld_x8(uint32_t addr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t addr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x16(uint32_t addr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -147,6 +157,8 @@ struct DevEnvTm {
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ int32_t ldg(const int32_t* p) const { return __ldg(p); }
     __device__ __forceinline__ double2 ldg2(const double2* p) const { return __ldg(p); }
+    __device__ __forceinline__ void tmem_ld8(int col, uint32_t (&w)[8]) const { tmem_ld_x8(tm_base + (uint32_t)col, w); }
+    __device__ __forceinline__ void tmem_st8(int col, const uint32_t (&w)[8]) const { tmem_st_x8(tm_base + (uint32_t)col, w); }
     __device__ __forceinline__ void tmem_ld16(int col, uint32_t (&w)[16]) const { tmem_ld_x16(tm_base + (uint32_t)col, w); }
     __device__ __forceinline__ void tmem_st16(int col, const uint32_t (&w)[16]) const { tmem_st_x16(tm_base + (uint32_t)col, w); }
     __device__ __forceinline__ void tmem_ld32(int col, uint32_t (&w)[32]) const { tmem_ld_x32(tm_base + (uint32_t)col, w); }

@@ -63,7 +63,8 @@ def default_params(minimum_lambda: int = 128) -> Params:
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "csrc", "libpeba1_cuda.so")
+    # PEBA1_CUDA_LIB: tuning aid (scripts/ablate.sh builds what-if variants of the kernels)
+    return os.environ.get("PEBA1_CUDA_LIB") or os.path.join(_HERE, "csrc", "libpeba1_cuda.so")
 
 
 _lib = None
