@@ -227,10 +227,14 @@ class Engine:
         p2 = _i64(np.ascontiguousarray(in2, dtype=np.int64)) if in2 is not None else None
         self._chk(self.L.peba1_cuda_gate_batch(self.h, OP[op], _i64(in0), _i64(in1), p2, _i64(out), out.size))
 
-    def gate_batch_host(self, op: str, ca, cb, cc=None) -> np.ndarray:
+    def gate_batch_host(self, op: str, ca, cb, cc=None, out=None) -> np.ndarray:
+        """peba1_cuda_gate_batch_host: host buffers in, host buffer out (`out` may be a preallocated, e.g. pinned,
+        int32 array of the same shape; a fresh pageable one costs page faults on every call)."""
         ca = np.ascontiguousarray(ca, dtype=np.int32).reshape(-1, self.words)
         cb = np.ascontiguousarray(cb, dtype=np.int32).reshape(-1, self.words)
-        out = np.empty_like(ca)
+        if out is None:
+            out = np.empty_like(ca)
+        assert out.dtype == np.int32 and out.flags["C_CONTIGUOUS"] and out.size == ca.size
         pc = None
         if cc is not None:
             cc = np.ascontiguousarray(cc, dtype=np.int32).reshape(-1, self.words)
