@@ -8,6 +8,8 @@
 #include <vector>
 #include "blind_rotate.cuh"
 #include "blind_rotate_tm.cuh"
+#include "blind_rotate_pair.cuh"
+#include "blind_rotate_tmk.cuh"
 #include "twiddles_host.h"
 
 using namespace peba1;
@@ -25,6 +27,8 @@ struct HostEnv {
     // tensor memory of the tensor-memory variant, emulated as a private array of 32-bit cells per thread
     int sums_col = 0;
     uint32_t* tm = nullptr;
+    void tmem_ld4(int col, uint32_t (&w)[4]) const { memcpy(w, tm + col, sizeof w); }
+    void tmem_st4(int col, const uint32_t (&w)[4]) const { memcpy(tm + col, w, sizeof w); }
     void tmem_ld8(int col, uint32_t (&w)[8]) const { memcpy(w, tm + col, sizeof w); }
     void tmem_st8(int col, const uint32_t (&w)[8]) const { memcpy(tm + col, w, sizeof w); }
     void tmem_ld16(int col, uint32_t (&w)[16]) const { memcpy(w, tm + col, sizeof w); }
@@ -33,6 +37,19 @@ struct HostEnv {
     void tmem_st32(int col, const uint32_t (&w)[32]) const { memcpy(tm + col, w, sizeof w); }
     void tmem_wait_ld() const {}
     void tmem_wait_st() const {}
+    // key pipeline of blind_rotate_tmk.cuh: the emulation reads the half-row straight from the transformed key
+    const double2* key = nullptr;
+    int key_rows = 0;
+    void key_pump(int) const {}
+    void key_wait(int) const {}
+    void key_release(int) const {}
+    void key_ld16(int h, int c, uint32_t (&k)[16]) const {
+        const int srow = h >> 1, half = h & 1;
+        for (int e = 0; e < 4; ++e) {
+            const double2 v = key[bkfft_index(key_rows, srow / key_rows, srow % key_rows, 4 * half + e, c, tid)];
+            c_to_words(v, k[4 * e], k[4 * e + 1], k[4 * e + 2], k[4 * e + 3]);
+        }
+    }
     // split-phase "exchange buffer free" barrier of the device code: a full team barrier is a valid (stronger) stand-in
     void ex1_acquire() { pthread_barrier_wait(team); }
     void ex1_release() {}
@@ -41,6 +58,7 @@ struct HostEnv {
 struct Shared {
     TeamSmem sm;
     TeamSmemTm sm_tm;
+    TeamSmemPair sm_pair;
     TwiddleTables tables;
     pthread_barrier_t team, warp[2];
     // work description
@@ -81,6 +99,37 @@ void* worker(void* p) {
                 blind_rotate_team_tm<3, 7>(env, S->sm_tm, S->bkfft, S->n, pool, S->n + 1, job, u);
             else
                 blind_rotate_team_tm<2, 10>(env, S->sm_tm, S->bkfft, S->n, pool, S->n + 1, job, u);
+        }
+    } else if (S->mode == 4) {
+        std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
+        env.tm = tmem.data();
+        env.sums_col = 64 * (A->tid % 4);
+        env.key = S->bkfft;
+        env.key_rows = S->rows;
+        tm_store_twiddles(env, tw);
+        for (int64_t g = 0; g < S->count; ++g) {
+            PbsJob job{(int32_t)g, -1, 0, 1, 0};
+            int32_t* u = S->u_out + (size_t)g * (kN + 1);
+            if (S->L == 3 && S->Bgbit == 7)
+                blind_rotate_team_tmk<3, 7>(env, S->sm_tm, S->n, S->in_ct, S->n + 1, job, true, u);
+            else
+                blind_rotate_team_tmk<2, 10>(env, S->sm_tm, S->n, S->in_ct, S->n + 1, job, true, u);
+        }
+    } else if (S->mode == 3) {
+        std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
+        env.tm = tmem.data();
+        env.sums_col = 128 * (A->tid % 2);
+        tm_store_twiddles(env, tw);
+        for (int64_t g = 0; g < S->count; g += 2) {  // pool = the input samples, job g reads slot g
+            PbsJob job0{(int32_t)g, -1, 0, 1, 0};
+            const bool two = g + 1 < S->count;
+            PbsJob job1{(int32_t)(two ? g + 1 : g), -1, 0, 1, 0};
+            int32_t* u0 = S->u_out + (size_t)g * (kN + 1);
+            int32_t* u1 = two ? u0 + (kN + 1) : nullptr;
+            if (S->L == 3 && S->Bgbit == 7)
+                blind_rotate_pair_tm<3, 7>(env, S->sm_pair, S->bkfft, S->n, S->in_ct, S->n + 1, job0, job1, u0, u1);
+            else
+                blind_rotate_pair_tm<2, 10>(env, S->sm_pair, S->bkfft, S->n, S->in_ct, S->n + 1, job0, job1, u0, u1);
         }
     } else {
         for (int64_t g = 0; g < S->count; ++g) {
@@ -142,6 +191,30 @@ int peba1_emu_bootstrap_woks_tm(int L, int Bgbit, int n, const double* bkfft, co
     if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
     Shared* S = new Shared();
     S->mode = 2; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
+    S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+// two bootstraps per team (blind_rotate_pair.cuh)
+int peba1_emu_bootstrap_woks_pair(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                                  int64_t count) {
+    if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
+    Shared* S = new Shared();
+    S->mode = 3; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
+    S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+// key rows through tensor memory (blind_rotate_tmk.cuh): consumer side only
+int peba1_emu_bootstrap_woks_tmk(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                                 int64_t count) {
+    if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
+    Shared* S = new Shared();
+    S->mode = 4; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
     S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
     int rc = run(S);
     delete S;

@@ -21,6 +21,8 @@
 
 #include "blind_rotate.cuh"
 #include "blind_rotate_tm.cuh"
+#include "blind_rotate_pair.cuh"
+#include "blind_rotate_tmk.cuh"
 #include "twiddles_host.h"
 
 using namespace peba1;
@@ -70,6 +72,14 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t addr, const uint32_t (&r)[8]
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t addr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_x16(uint32_t addr, uint32_t (&r)[16]) {
     asm volatile(
@@ -157,6 +167,8 @@ struct DevEnvTm {
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
     __device__ __forceinline__ int32_t ldg(const int32_t* p) const { return __ldg(p); }
     __device__ __forceinline__ double2 ldg2(const double2* p) const { return __ldg(p); }
+    __device__ __forceinline__ void tmem_ld4(int col, uint32_t (&w)[4]) const { tmem_ld_x4(tm_base + (uint32_t)col, w); }
+    __device__ __forceinline__ void tmem_st4(int col, const uint32_t (&w)[4]) const { tmem_st_x4(tm_base + (uint32_t)col, w); }
     __device__ __forceinline__ void tmem_ld8(int col, uint32_t (&w)[8]) const { tmem_ld_x8(tm_base + (uint32_t)col, w); }
     __device__ __forceinline__ void tmem_st8(int col, const uint32_t (&w)[8]) const { tmem_st_x8(tm_base + (uint32_t)col, w); }
     __device__ __forceinline__ void tmem_ld16(int col, uint32_t (&w)[16]) const { tmem_ld_x16(tm_base + (uint32_t)col, w); }
@@ -165,6 +177,88 @@ struct DevEnvTm {
     __device__ __forceinline__ void tmem_st32(int col, const uint32_t (&w)[32]) const { tmem_st_x32(tm_base + (uint32_t)col, w); }
     __device__ __forceinline__ void tmem_wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
     __device__ __forceinline__ void tmem_wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+};
+
+// Key pipeline producer (see blind_rotate_tmk.cuh): one thread of a dedicated 17th warp.
+// Barriers (8 bytes each, from `bars`): tma_full[3] @0, smem_free[3] @24, tmem_full[4] @48, tmem_free[4] @80.
+__device__ __forceinline__ void mbar_wait_parity(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// The producer thread shares its scheduler with four compute warps: it must not spin at full rate (measured: 214 M
+// failed polls per launch = a fifth of that scheduler's issue slots, and its four warps become the CTA's laggards).
+__device__ __forceinline__ void mbar_wait_parity_sleep(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void key_issue_tma(uint32_t bars, uint32_t stage, const unsigned char* key, int g) {
+    const int slot = g % 3, use = g / 3;
+    if (use >= 1) mbar_wait_parity_sleep(bars + 24u + 8u * (uint32_t)slot, (uint32_t)(use - 1) & 1u);  // smem_free
+    const uint32_t dst = stage + (uint32_t)slot * (uint32_t)kKeyHalfBytes;
+    const uint32_t full = bars + 8u * (uint32_t)slot;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)kKeyHalfBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(key + (size_t)g * kKeyHalfBytes), "r"((uint32_t)kKeyHalfBytes), "r"(full) : "memory");
+}
+__device__ __noinline__ void key_producer_loop(uint32_t tm_alloc, uint32_t bars, uint32_t stage, const unsigned char* key,
+                                               int total_half) {
+    for (int g = 0; g < 2 && g < total_half; ++g) key_issue_tma(bars, stage, key, g);
+    for (int h = 0; h < total_half; ++h) {
+        const int slot = h % 3, use = h / 3;
+        mbar_wait_parity_sleep(bars + 8u * (uint32_t)slot, (uint32_t)use & 1u);                                     // tma_full
+        if (h >= 4) mbar_wait_parity_sleep(bars + 80u + 8u * (uint32_t)(h & 3), (uint32_t)((h >> 2) - 1) & 1u);      // tmem_free
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t src = stage + (uint32_t)slot * (uint32_t)kKeyHalfBytes;
+        const uint32_t dst = tm_alloc + (uint32_t)(kTmKey + 32 * (h & 3));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // block j = 2 * (k2 & 3) + c: 64 thread indices x 16 bytes
+            // matrix descriptor: start >> 4, LBO 0, SBO 128 B (8-row x 16-byte atoms, contiguous), version 1, no swizzle
+            const uint64_t desc = (uint64_t)(((src + 1024u * (uint32_t)j) & 0x3FFFFu) >> 4) |
+                                  ((uint64_t)(128u >> 4) << 32) | ((uint64_t)1 << 46);
+            asm volatile("tcgen05.cp.cta_group::1.64x128b.warpx2::02_13 [%0], %1;"
+                         ::"r"(dst + (uint32_t)(16 * (j & 1) + 4 * (j >> 1))), "l"(desc) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     ::"r"(bars + 48u + 8u * (uint32_t)(h & 3)) : "memory");   // tmem_full
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     ::"r"(bars + 24u + 8u * (uint32_t)slot) : "memory");      // smem_free
+        // refill the slot half-row h-1 was copied from (its copies were issued one iteration ago: done by now)
+        if (h + 2 < total_half) key_issue_tma(bars, stage, key, h + 2);
+    }
+}
+
+// Environment of the key-through-tensor-memory kernel (blind_rotate_tmk.cuh): DevEnvTm + the consumer side of the
+// key pipeline.
+struct DevEnvTmk : DevEnvTm {
+    uint32_t bars = 0;  // smem address of the 14 mbarriers
+    __device__ __forceinline__ void key_pump(int) const {}
+    __device__ __forceinline__ void key_wait(int h) const {
+        mbar_wait_parity(bars + 48u + 8u * (uint32_t)(h & 3), (uint32_t)(h >> 2) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    __device__ __forceinline__ void key_ld16(int h, int c, uint32_t (&k)[16]) const {
+        tmem_ld_x16(tm_base + (uint32_t)(kTmKey + 32 * (h & 3) + 16 * c), k);
+    }
+    __device__ __forceinline__ void key_release(int h) const {  // after the tcgen05.wait::ld that covers the loads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0)
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bars + 80u + 8u * (uint32_t)(h & 3)) : "memory");
+    }
 };
 
 __constant__ TwiddleTables c_tables;
@@ -303,6 +397,127 @@ __global__ void __launch_bounds__(kTeamsTm* kTeam, 1)
     if (!live) g = count - 1;  // a team without a job shadows the last one: it must still feed its group
     blind_rotate_team_tmsh<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g], live,
                                      u_out + g * (int64_t)kUStride);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_alloc_base));
+}
+
+// K0+K1, pair version (blind_rotate_pair.cuh): TEAMS teams of 64 threads, TWO bootstraps per team; 4 teams = 8 warps
+// per SM with up to 255 registers.  Job index = 2 * (blockIdx.x * TEAMS + team) (+1).
+constexpr int kTeamsPair = 4;
+template <int L, int BGBIT, int TEAMS>
+__global__ void __launch_bounds__(TEAMS* kTeam, 1)
+    pbs_kernel_pair(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
+                    const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TeamSmemPair* teams = reinterpret_cast<TeamSmemPair*>(smem_raw);
+    __shared__ uint32_t tm_alloc_base;
+    const int warp = threadIdx.x >> 5;
+    const int team = threadIdx.x / kTeam;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"l"(
+            (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if ((threadIdx.x % kTeam) == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"((uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 128 * (warp >> 2),
+                 tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16)};
+    env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
+    // one warp per lane quarter publishes the per-thread twiddles: with fewer than 4 warps (TEAMS == 1) quarters 2 and 3
+    // are never touched
+    if ((warp >> 2) == 0) {
+        TeamTwiddles tw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            tw.tw1[j] = c_tables.tw1[env.tid][j];
+            tw.tw2[j] = c_tables.tw2[env.tid & 7][j];
+        }
+        tm_store_twiddles(env, tw);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int64_t g = 2 * ((int64_t)blockIdx.x * TEAMS + team);
+    if (g < count) {
+        const bool two = g + 1 < count;
+        blind_rotate_pair_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g], jobs[two ? g + 1 : g],
+                                       u_out + g * (int64_t)kUStride,
+                                       two ? u_out + (g + 1) * (int64_t)kUStride : nullptr);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_alloc_base));
+}
+
+// K0+K1, key-through-tensor-memory version (blind_rotate_tmk.cuh): 8 teams (16 warps) + a 17th warp whose lane 0 streams
+// every key row once per CTA with TMA + tcgen05.cp (544 threads => 120 registers).  Dynamic smem: [3 x 8 KB key
+// staging][8 x TeamSmemTm].
+constexpr int kTmkThreads = kTeamsTm * kTeam + 32;
+template <int L, int BGBIT>
+__global__ void __launch_bounds__(kTmkThreads, 1)
+    pbs_kernel_tmk(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
+                   const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TeamSmemTm* teams = reinterpret_cast<TeamSmemTm*>(smem_raw + 3 * kKeyHalfBytes);
+    __shared__ uint32_t tm_alloc_base;
+    __shared__ __align__(8) uint64_t key_bars[14];
+    const int warp = threadIdx.x >> 5;
+    const int team = threadIdx.x / kTeam;  // 8 = the producer warp
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"l"(
+            (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (team < kTeamsTm && (threadIdx.x % kTeam) == 0)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"((uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free)));
+    if (threadIdx.x == 32) {
+        for (int b = 0; b < 14; ++b)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&key_bars[b])),
+                         "r"(b >= 10 ? 2 * kTeamsTm : 1));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int total_half = n * 2 * L * 2;
+    if (team < kTeamsTm) {
+        DevEnvTmk env;
+        env.tid = (int)(threadIdx.x % kTeam);
+        env.bar_id = team + 1;
+        env.sums_col = kTmSums + 64 * (warp >> 2);
+        env.tm_base = tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16);
+        env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
+        env.bars = (uint32_t)__cvta_generic_to_shared(&key_bars[0]);
+        if ((warp >> 2) == 0) {
+            TeamTwiddles tw;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                tw.tw1[j] = c_tables.tw1[env.tid][j];
+                tw.tw2[j] = c_tables.tw2[env.tid & 7][j];
+            }
+            tm_store_twiddles(env, tw);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 15, %0;" ::"n"(kTeamsTm * kTeam) : "memory");  // the 16 compute warps: twiddles are published
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        int64_t g = (int64_t)blockIdx.x * kTeamsTm + team;
+        const bool live = g < count;
+        if (!live) g = count - 1;  // a team without a job shadows the last one: it must still consume the key rows
+        blind_rotate_team_tmk<L, BGBIT>(env, teams[team], n, pool, pool_stride, jobs[g], live,
+                                        u_out + g * (int64_t)kUStride);
+    } else if ((threadIdx.x & 31) == 0) {
+        key_producer_loop(tm_alloc_base, (uint32_t)__cvta_generic_to_shared(&key_bars[0]),
+                          (uint32_t)__cvta_generic_to_shared(smem_raw), reinterpret_cast<const unsigned char*>(bkfft),
+                          total_half);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -514,7 +729,9 @@ struct peba1_cuda_ctx {
     int teams_per_cta = 6;
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
-    int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default)
+    int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default),
+                             // 2: shared-key, 3: two bootstraps per team (blind_rotate_pair.cuh) for wide batches
+    int64_t pair_min_batch = -1;  // variant 3 below this batch size falls back to variant 1; -1 = 8 per SM
     int64_t max_pbs_per_launch = 1 << 18;
     // stats
     bool timing = false;
@@ -600,6 +817,24 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         auto k = pbs_kernel_tmsh<L, BGBIT>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+        return 0;
+    }
+    if (c->kernel_variant == 4 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
+        const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm + 3 * kKeyHalfBytes;
+        const unsigned grid = (unsigned)((count + kTeamsTm - 1) / kTeamsTm);
+        auto k = pbs_kernel_tmk<L, BGBIT>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTmkThreads, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+        return 0;
+    }
+    if (c->kernel_variant == 3 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * 2 * kTeamsPair)) {
+        const size_t smem = sizeof(TeamSmemPair) * (size_t)kTeamsPair;
+        const unsigned grid = (unsigned)((count + 2 * kTeamsPair - 1) / (2 * kTeamsPair));
+        auto k = pbs_kernel_pair<L, BGBIT, kTeamsPair>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsPair * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
         return 0;
     }
     // Narrow levels (the long tail of a circuit: tens of gates per launch) cannot fill 148 SMs with 8 bootstraps per
@@ -749,7 +984,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
-    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 2 ? atoi(v) : 1;  // tuning aid
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 4 ? atoi(v) : 1;  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
@@ -1188,8 +1423,12 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         c->ks_group = (int)value;
         return 0;
     }
+    if (!strcmp(name, "pair_min_batch")) {
+        c->pair_min_batch = value;
+        return 0;
+    }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 2) return fail(PEBA1_EINVAL, "kernel_variant must be 0, 1 or 2");
+        if (value < 0 || value > 4) return fail(PEBA1_EINVAL, "kernel_variant must be 0..4");
         c->kernel_variant = (int)value;
         return 0;
     }

@@ -175,6 +175,12 @@ def test_kernel_variants_agree(engine, keys):
         for variant in (0, 1, 2):
             engine.set_option("kernel_variant", variant)
             assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), variant
+        engine.set_option("pair_min_batch", 1)   # two bootstraps per team; n is odd: the last team carries a shadow
+        engine.set_option("kernel_variant", 3)
+        assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), "pair"
+        assert np.array_equal(engine.gate_batch_host("ANDYN", ca[:1], cb[:1]), want[:1]), "pair, single"
+        engine.set_option("kernel_variant", 4)   # key rows through TMA + tcgen05.cp; 45 jobs: the last CTA has shadow teams
+        assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), "tmk"
         engine.set_option("kernel_variant", 1)
         for teams in (1, 2, 4, 8):
             engine.set_option("tm_teams", teams)
@@ -186,3 +192,4 @@ def test_kernel_variants_agree(engine, keys):
         engine.set_option("kernel_variant", 1)
         engine.set_option("tm_teams", 0)
         engine.set_option("ks_group", 1)
+        engine.set_option("pair_min_batch", -1)
