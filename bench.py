@@ -27,6 +27,10 @@ sys.path.insert(0, ROOT)
 F_PBS = 630 * 258048            # FP64 flops per bootstrap: 162,570,240
 KSK_BYTES = 62029824            # non-zero keyswitch-key rows, unpadded
 KEY_SEED = 42
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this very
+# command at batch 16,384 (profiles/r1k_pbs_kernel_tm_ncu.txt, profiles/r1k_keyswitch_kernel_ncu.txt); reported as
+# roofline.traffic when the run uses that batch, null otherwise.
+NCU_TRAFFIC = {16384: {"blind_rotate": 775191296 + 70773760, "keyswitch": 413619968 + 43149824}}
 
 
 def parse():
@@ -40,7 +44,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the CPU baseline sample (0: cores*512, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-face-match", action="store_true")
-    ap.add_argument("--face-templates", type=int, default=2, help="templates per GPU in the face-match leg (0: skip)")
+    ap.add_argument("--no-other-ops", action="store_true", help="skip the XOR / MUX legs of configs[1]")
+    ap.add_argument("--face-templates", type=int, default=8, help="templates per GPU in the face-match leg (0: skip)")
     return ap.parse_args()
 
 
@@ -312,6 +317,39 @@ def main():
     if rank == 0:
         verified = verified and bool(np.array_equal(ks.decrypt(pinned_out.numpy()), want))
 
+    # ---- the other two gate types configs[1] names, same batch, device-resident (2 warm-up + 2 timed launches each)
+    other = {}
+    if not args.no_other_ops:
+        eng.enable_timing(True)
+        for op in ("NAND", "XOR", "MUX"):
+            if op == args.op:
+                continue
+            n_in = 3 if op == "MUX" else 2
+            eng.reserve(base + (n_in + 1) * B)
+            if n_in > nin:                              # MUX needs a third operand block: device-side encryption
+                if rank == 0:
+                    eng.encrypt_bits(ks.lwe_key, rng.integers(0, 2, size=B), base + 2 * B, seed=78)
+                else:
+                    eng.upload(base + 2 * B, rng.integers(-2**31, 2**31, size=(B, words), dtype=np.int64).astype(np.int32))
+            g2 = make_gates(op, idx, B + idx, n_in * B + idx, in2=(2 * B + idx) if op == "MUX" else None)
+            for _ in range(2):
+                eng.gates(g2)
+            eng.reset_stats()
+            barrier()
+            e0.record(stream)
+            for _ in range(2):
+                eng.gates(g2)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_op = float(t.item()) / 2
+            per = 2 if op == "MUX" else 1
+            other[op] = {"gpu_launches": int(eng.stats().launches), "pbs_per_s": world * B * per / (ms_op * 1e-3), "gates_per_s": world * B / (ms_op * 1e-3),
+                         "ms_per_step": ms_op, "pbs_per_gate": per}
+        eng.enable_timing(False)
+
     # ---- encrypted face matches/s on a bounded number of templates per GPU
     face = face_opt = None
     if not args.no_face_match and args.face_templates > 0:
@@ -359,14 +397,17 @@ def main():
         "gpu_launches": launches,
         "kernel_ms": {"blind_rotate": br_ms, "keyswitch": ks_ms},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp64_peak, "traffic": None,
+                     "frac": achieved_tf / fp64_peak, "traffic": NCU_TRAFFIC.get(B, {}).get("blind_rotate"),
                      "note": "dominant kernel = blind rotation (FP64 vector pipe; neither hbm nor tensor applies). "
                              "achieved = 162,570,240 flop/PBS x PBS per launch / CUDA-event time of the launch; peak = "
-                             "DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry)"},
+                             "DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); traffic = "
+                             "DRAM bytes per launch from profiles/r1k_pbs_kernel_tm_ncu.txt (the key stays L2-resident)"},
         "roofline_keyswitch": {"bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                               "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                               "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak,
+                               "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"),
                                "note": "algorithmic bytes = 62.0 MB key + batch x (4100 in + 2524 out); peak = "
                                        "MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
+        "other_ops": other or None,
         "face_match": face,
         "face_match_optimised": face_opt,
         "cpu_baseline": cpu,

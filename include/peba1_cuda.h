@@ -95,6 +95,13 @@ int peba1_cuda_download(peba1_cuda_ctx* ctx, int64_t first_slot, int64_t count, 
 int peba1_cuda_upload_slots(peba1_cuda_ctx* ctx, const int64_t* slots, int64_t count, const int32_t* host);
 int peba1_cuda_download_slots(peba1_cuda_ctx* ctx, const int64_t* slots, int64_t count, int32_t* host);
 
+/* Device-side encryption of `count` bits (what bootsSymEncrypt, src/main.cpp:64, does per bit):
+   slot slots[i] (or first_slot + i when slots is NULL) <- LWE encryption of bits[i] under lwe_key (n words, 0/1) with
+   noise sigma.  Counter-based generator: the result depends only on (seed, index0 + i).  For synthetic galleries and
+   benchmark inputs: it places the SECRET key on the device, which a deployment never does (clients encrypt). */
+int peba1_cuda_encrypt_bits(peba1_cuda_ctx* ctx, const int32_t* lwe_key, const int32_t* bits, const int64_t* slots,
+                            int64_t first_slot, int64_t count, int64_t index0, uint64_t seed, double sigma);
+
 /* One circuit level: `count` independent gates, executed as one blind-rotation launch (K0+K1) and one
    keyswitch launch (K2).  Asynchronous on the context stream. */
 int peba1_cuda_gates(peba1_cuda_ctx* ctx, const peba1_gate* gates, int64_t count);

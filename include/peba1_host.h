@@ -59,6 +59,7 @@ typedef struct {
     uint64_t executed_gates, executed_pbs; /* what was actually launched (differs from gates/pbs in fold mode) */
     uint64_t folded;       /* gates replaced by a constant, an alias or a cheaper gate at record time (fold mode) */
     uint64_t dead;         /* recorded gates dropped at flush because nothing consumed them (fold mode) */
+    uint64_t device_encryptions; /* ciphertexts produced by peba1_encrypt_array_device */
 } peba1_host_stats;
 void peba1_get_stats(peba1_host_stats* out);
 void peba1_reset_stats(void);
@@ -83,6 +84,14 @@ const int32_t* peba1_keyset_bk(const TFheGateBootstrappingCloudKeySet* bk);   /*
 const int32_t* peba1_keyset_ksk(const TFheGateBootstrappingCloudKeySet* bk);  /* [N][t][2^basebit][n+1] */
 /* Batch encryption with an explicit seed: bits[count] -> words[count][n+1]. */
 void peba1_encrypt_bits(const TFheGateBootstrappingSecretKeySet* key, const int32_t* bits, int64_t count, uint64_t seed, int32_t* words);
+/* array[i] <- fresh encryption of bits[i] made ON THE DEVICE (peba1_cuda_encrypt_bits): synthetic galleries and benchmark
+   inputs without host->device traffic.  Deterministic per (seed, i).  Hands the secret LWE key to the GPU: benchmark
+   and test use only. */
+void peba1_encrypt_array_device(LweSample* array, int32_t nbelems, const int32_t* bits,
+                                const TFheGateBootstrappingSecretKeySet* key, uint64_t seed);
+/* The same for a list of arrays (arrays[k][i] <- bits[k * nbelems + i]) in ONE launch: a wave of templates. */
+void peba1_encrypt_array_list_device(LweSample* const* arrays, int32_t narrays, int32_t nbelems, const int32_t* bits,
+                                     const TFheGateBootstrappingSecretKeySet* key, uint64_t seed);
 void peba1_decrypt_words(const TFheGateBootstrappingSecretKeySet* key, const int32_t* words, int64_t count, int32_t* bits);
 /* The libpeba1_cuda context behind a cloud key (created on first use); NULL without a device. */
 void* peba1_cuda_context_of(const TFheGateBootstrappingCloudKeySet* bk);

@@ -464,7 +464,7 @@ constexpr int kTmkThreads = kTeamsTm * kTeam + 32;
 template <int L, int BGBIT>
 __global__ void __launch_bounds__(kTmkThreads, 1)
     pbs_kernel_tmk(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
-                   const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+                   const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out, int stagger_ns) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TeamSmemTm* teams = reinterpret_cast<TeamSmemTm*>(smem_raw + 3 * kKeyHalfBytes);
     __shared__ uint32_t tm_alloc_base;
@@ -511,6 +511,9 @@ __global__ void __launch_bounds__(kTmkThreads, 1)
         int64_t g = (int64_t)blockIdx.x * kTeamsTm + team;
         const bool live = g < count;
         if (!live) g = count - 1;  // a team without a job shadows the last one: it must still consume the key rows
+        // The shared key ring keeps the teams within two rows of each other; started together they stay in phase and
+        // hit the FP64 pipe and the exchange buffers in bursts.  A start-up stagger spreads them over a row.
+        if (stagger_ns > 0) __nanosleep((unsigned)(stagger_ns * team));
         blind_rotate_team_tmk<L, BGBIT>(env, teams[team], n, pool, pool_stride, jobs[g], live,
                                         u_out + g * (int64_t)kUStride);
     } else if ((threadIdx.x & 31) == 0) {
@@ -522,6 +525,63 @@ __global__ void __launch_bounds__(kTmkThreads, 1)
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_alloc_base));
+}
+
+// Device-side encryption: synthetic gallery / benchmark inputs generated where they are used
+// instead of 2.5 KB per bit over PCIe.  One warp per ciphertext; counter-based generator (Philox4x32-10, keyed by the
+// seed, counter = ciphertext index and word block), so the output depends only on (seed, index), not on the launch
+// shape.  c = (a, <a,s> + e + mu), a uniform, e = round(N(0, sigma) * 2^32), mu = +-1/8: TFHE's bootsSymEncrypt
+// (src/main.cpp:64).  TEST / BENCHMARK use: it needs the secret LWE key on the device.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256)
+    lwe_encrypt_kernel(int32_t* __restrict__ pool, int64_t stride, const int64_t* __restrict__ slots, int64_t first_slot,
+                       const int32_t* __restrict__ bits, int64_t count, int64_t index0, int n,
+                       const uint32_t* __restrict__ keymask, uint64_t seed, double sigma) {
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= count) return;
+    const int64_t slot = slots ? slots[g] : first_slot + g;
+    int32_t* row = pool + slot * stride;
+    const uint64_t idx = (uint64_t)(index0 + g);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t sum = 0;
+    for (int q = lane; 4 * q < stride; q += 32) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)q, 0u, k0, k1, r);
+        const uint32_t km = keymask[q >> 3] >> (4 * (q & 7));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int w = 4 * q + j;
+            if (w >= n) r[j] = 0u;                 // body (written below) and padding
+            else if ((km >> j) & 1u) sum += r[j];
+        }
+        *reinterpret_cast<int4*>(row + 4 * q) = make_int4((int)r[0], (int)r[1], (int)r[2], (int)r[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    if (lane == 0) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), 0xFFFFFFFFu, 1u, k0, k1, r);
+        // Box-Muller on two 32-bit uniforms in (0,1]
+        const double u1 = ((double)r[0] + 1.0) * (1.0 / 4294967296.0), u2 = (double)r[1] * (1.0 / 4294967296.0);
+        const double z = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        const double d = z * sigma;
+        const uint32_t e = (uint32_t)(int32_t)(int64_t)((d - (double)(int64_t)d) * 4294967296.0);
+        const uint32_t mu = bits[g] ? (1u << 29) : 0u - (1u << 29);
+        row[n] = (int32_t)(sum + e + mu);
+    }
 }
 
 // K3.  One team per key polynomial q = (i*rows + r)*2 + c.
@@ -731,6 +791,7 @@ struct peba1_cuda_ctx {
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default),
                              // 2: shared-key, 3: two bootstraps per team (blind_rotate_pair.cuh) for wide batches
+    int tmk_stagger_ns = 0;       // variant 4: start-up delay per team index
     int64_t pair_min_batch = -1;  // variant 3 below this batch size falls back to variant 1; -1 = 8 per SM
     int64_t max_pbs_per_launch = 1 << 18;
     // stats
@@ -825,7 +886,7 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         const unsigned grid = (unsigned)((count + kTeamsTm - 1) / kTeamsTm);
         auto k = pbs_kernel_tmk<L, BGBIT>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kTmkThreads, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+        k<<<grid, kTmkThreads, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->tmk_stagger_ns);
         return 0;
     }
     if (c->kernel_variant == 3 &&
@@ -1366,6 +1427,41 @@ int peba1_cuda_keyswitch_host(peba1_cuda_ctx* c, const int32_t* in_extracted, in
     return peba1_cuda_download(c, 0, count, out);
 }
 
+int peba1_cuda_encrypt_bits(peba1_cuda_ctx* c, const int32_t* lwe_key, const int32_t* bits, const int64_t* slots,
+                            int64_t first_slot, int64_t count, int64_t index0, uint64_t seed, double sigma) {
+    if (int rc = use_device(c)) return rc;
+    if (count < 0 || !lwe_key || (count > 0 && !bits)) return fail(PEBA1_EINVAL, "bad encryption request");
+    if (count == 0) return 0;
+    if (!slots && (first_slot < 0 || first_slot + count > c->pool_slots))
+        return fail(PEBA1_EINVAL, "slot range [%lld, +%lld) outside the pool", (long long)first_slot, (long long)count);
+    if (slots)
+        for (int64_t i = 0; i < count; ++i)
+            if (slots[i] < 0 || slots[i] >= c->pool_slots) return fail(PEBA1_EINVAL, "slot %lld outside the pool", (long long)slots[i]);
+    uint32_t mask[32] = {0};  // key bit w at bit (w & 31) of word w >> 5: the kernel reads 4 bits per word quad
+    for (int w = 0; w < c->p.n; ++w)
+        if (lwe_key[w]) mask[w >> 5] |= 1u << (w & 31);
+    const size_t bytes = sizeof mask + (size_t)count * sizeof(int32_t) + 8 + (slots ? (size_t)count * sizeof(int64_t) : 0);
+    unsigned char* d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    CU(cudaMemcpyAsync(d, mask, sizeof mask, cudaMemcpyHostToDevice, c->stream));
+    int32_t* d_bits = reinterpret_cast<int32_t*>(d + sizeof mask);
+    CU(cudaMemcpyAsync(d_bits, bits, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    int64_t* d_slots = nullptr;
+    if (slots) {
+        d_slots = reinterpret_cast<int64_t*>(d + sizeof mask + (((size_t)count * sizeof(int32_t) + 7) & ~(size_t)7));
+        // the int64 array needs 8-byte alignment: the allocation is 256-byte aligned and sizeof mask is 128
+        CU(cudaMemcpyAsync(d_slots, slots, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    const unsigned grid = (unsigned)((count + 7) / 8);
+    lwe_encrypt_kernel<<<grid, 256, 0, c->stream>>>(c->pool, c->pool_stride, d_slots, first_slot, d_bits, count, index0,
+                                                    c->p.n, reinterpret_cast<const uint32_t*>(d), seed, sigma);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    return 0;
+}
+
 int peba1_cuda_enable_timing(peba1_cuda_ctx* c, int enable) {
     if (!c) return fail(PEBA1_EINVAL, "null context");
     c->timing = enable != 0;
@@ -1421,6 +1517,10 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         if (value == 0) value = 1;
         if (value != 1 && value != 2 && value != 4 && value != 6 && value != 8) return fail(PEBA1_EINVAL, "ks_group must be 1, 2, 4, 6 or 8");
         c->ks_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "tmk_stagger_ns")) {
+        c->tmk_stagger_ns = (int)value;
         return 0;
     }
     if (!strcmp(name, "pair_min_batch")) {

@@ -20,7 +20,8 @@ DECLARED_SYMBOLS = [
     "peba1_cuda_set_stream", "peba1_cuda_sync", "peba1_cuda_load_bootstrap_key", "peba1_cuda_load_keyswitch_key",
     "peba1_cuda_key_device_buffers", "peba1_cuda_keys_mark_loaded", "peba1_cuda_pool_reserve",
     "peba1_cuda_pool_info", "peba1_cuda_upload", "peba1_cuda_download", "peba1_cuda_upload_slots",
-    "peba1_cuda_download_slots", "peba1_cuda_gates", "peba1_cuda_gate_batch", "peba1_cuda_gate_batch_host",
+    "peba1_cuda_download_slots", "peba1_cuda_encrypt_bits", "peba1_cuda_gates", "peba1_cuda_gate_batch",
+    "peba1_cuda_gate_batch_host",
     "peba1_cuda_linear", "peba1_cuda_bootstrap_woks_host", "peba1_cuda_keyswitch_host",
     "peba1_cuda_enable_timing", "peba1_cuda_get_stats", "peba1_cuda_reset_stats",
     "peba1_cuda_measure_fp64_peak", "peba1_cuda_set_option",
@@ -99,6 +100,7 @@ def load_library():
     L.peba1_cuda_upload_slots.argtypes = [vp, i64p, C.c_int64, i32p]
     L.peba1_cuda_download_slots.argtypes = [vp, i64p, C.c_int64, i32p]
     L.peba1_cuda_gates.argtypes = [vp, vp, C.c_int64]
+    L.peba1_cuda_encrypt_bits.argtypes = [vp, i32p, i32p, i64p, C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_double]
     L.peba1_cuda_gate_batch.argtypes = [vp, C.c_int32, i64p, i64p, i64p, i64p, C.c_int64]
     L.peba1_cuda_gate_batch_host.argtypes = [vp, C.c_int32, i32p, i32p, i32p, i32p, C.c_int64]
     L.peba1_cuda_linear.argtypes = [vp, i64p, i32p, i32p, i64p, C.c_int64]
@@ -213,6 +215,14 @@ class Engine:
         out = np.empty((slots.size, self.words), dtype=np.int32)
         self._chk(self.L.peba1_cuda_download_slots(self.h, _i64(slots), slots.size, _i32(out.reshape(-1))))
         return out
+
+    def encrypt_bits(self, lwe_key, bits, first_slot: int, seed: int, sigma: float = 2.0 ** -15, slots=None, index0: int = 0):
+        """Device-side encryption of `bits` into consecutive slots from `first_slot` (or into `slots`)."""
+        key = np.ascontiguousarray(lwe_key, dtype=np.int32)
+        bits = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)
+        sl = None if slots is None else np.ascontiguousarray(slots, dtype=np.int64)
+        self._chk(self.L.peba1_cuda_encrypt_bits(self.h, _i32(key), _i32(bits), None if sl is None else _i64(sl),
+                                                 first_slot, bits.size, index0, seed, sigma))
 
     # ---- gates
     def gates(self, gates: np.ndarray):

@@ -40,6 +40,24 @@ def synthetic_gallery(total: int, slots: int = 128, seed: int = 2024, planted: f
     return probe, gallery, (dist2 > bound).astype(np.int64)
 
 
+def synthetic_gallery_shard(total: int, lo: int, hi: int, slots: int = 128, seed: int = 2024, planted: float = 0.25,
+                            bound: int = 512):
+    """Templates [lo, hi) of a `total`-template gallery whose template t depends on (seed, t) only, so each rank
+    makes its own shard (BASELINE configs[4]: 65,536 templates) without anyone holding the whole gallery.  Same
+    planting rule and polarity as synthetic_gallery.  Returns (probe, templates [hi-lo, slots], expected bits)."""
+    probe = np.random.default_rng([seed, 0xFACE]).integers(1, 256, size=slots)
+    period = max(1, int(round(1 / planted))) if planted > 0 else 0
+    gallery = np.empty((hi - lo, slots), dtype=np.int64)
+    for t in range(lo, hi):
+        rng = np.random.default_rng([seed, t])
+        if period and t % period == 1:
+            gallery[t - lo] = np.clip(probe + rng.integers(-2, 3, size=slots), 0, 255)
+        else:
+            gallery[t - lo] = rng.integers(0, 256, size=slots)
+    dist2 = ((gallery - probe) ** 2).sum(axis=1)
+    return probe, gallery, (dist2 > bound).astype(np.int64)
+
+
 def distribute(dist, rank: int, world: int, device, torch, words: int, slots: int, bits: int, per_rank: int,
                client=None):
     """client = (probe_words [slots*bits, words], bound_words [24, words], gallery_words [world*per_rank, slots*bits,
@@ -63,36 +81,61 @@ def distribute(dist, rank: int, world: int, device, torch, words: int, slots: in
     return probe_t.cpu().numpy(), bound_t.cpu().numpy(), mine_t.cpu().numpy()
 
 
-def match_templates(ks: "H.KeySet", probe_w, bound_w, templates_w, slots: int = 128, bits: int = 8) -> np.ndarray:
-    """Function_f(probe, template_t, bound) for every local template, one batch; returns the comparator-bit
-    ciphertexts [T, words]."""
-    L = H.load_library()
+def _host_vector(ks, w, slots: int, bits: int):
     LSP = C.POINTER(H.LweSample)
+    arrs = []
+    for i in range(slots):
+        a = ks.new_array(bits)
+        ks.set_words(a, w[i * bits:(i + 1) * bits])
+        arrs.append(a)
+    return arrs, (LSP * slots)(*arrs)
 
-    def vec(w):
-        arrs = []
-        for i in range(slots):
-            a = ks.new_array(bits)
-            ks.set_words(a, w[i * bits:(i + 1) * bits])
-            arrs.append(a)
-        return arrs, (LSP * slots)(*arrs)
-    pa, pp = vec(probe_w)
+
+def encrypt_templates_on_device(ks: "H.KeySet", templates: np.ndarray, bits: int = 8, seed: int = 1):
+    """Plaintext templates [T, slots] -> per template a vector of `slots` ciphertext arrays whose encryptions are made
+    on the GPU (peba1_encrypt_array_device): nothing but the plaintext bits crosses PCIe.  Benchmark-side stand-in for
+    the clients who would upload their encrypted templates."""
+    LSP = C.POINTER(H.LweSample)
+    out = []
+    T, slots = templates.shape
+    flat = []
+    for t in range(T):
+        arrs = [ks.new_array(bits) for _ in range(slots)]
+        flat.extend(arrs)
+        out.append((arrs, (LSP * slots)(*arrs)))
+    if flat:
+        ks.encrypt_array_list_device(flat, bits, bits_of(templates.reshape(-1), bits), seed)  # one launch per wave
+    return out
+
+
+def match_template_arrays(ks: "H.KeySet", probe_w, bound_w, template_vecs, slots: int = 128, bits: int = 8) -> np.ndarray:
+    """Function_f(probe, template_t, bound) for every template vector in `template_vecs` (as made by _host_vector or
+    encrypt_templates_on_device), ONE batch: each of the 377 circuit levels is one launch pair.  Frees the template
+    arrays; returns the comparator-bit ciphertexts [T, words]."""
+    L = H.load_library()
+    pa, pp = _host_vector(ks, probe_w, slots, bits)
     eb = ks.new_array(24)
     ks.set_words(eb, bound_w)
-    T = templates_w.shape[0]
-    tv = [vec(templates_w[t]) for t in range(T)]
+    T = len(template_vecs)
     rb = [ks.new_array(24) for _ in range(T)]
     L.peba1_batch_begin()
     for t in range(T):
-        L.peba1_math_function_f(rb[t], pp, tv[t][1], slots, eb, bits, ks.cloud)
+        L.peba1_math_function_f(rb[t], pp, template_vecs[t][1], slots, eb, bits, ks.cloud)
     L.peba1_batch_end()
     out = np.stack([ks.get_words(rb[t], 1)[0] for t in range(T)]) if T else np.zeros((0, ks.words), np.int32)
-    for arrs, _ in tv + [(pa, pp)]:
+    for arrs, _ in list(template_vecs) + [(pa, pp)]:
         for a in arrs:
             ks.free_array(bits, a)
     for a in rb + [eb]:
         ks.free_array(24, a)
     return out
+
+
+def match_templates(ks: "H.KeySet", probe_w, bound_w, templates_w, slots: int = 128, bits: int = 8) -> np.ndarray:
+    """As match_template_arrays, from host ciphertext words [T, slots*bits, words] (uploaded)."""
+    return match_template_arrays(ks, probe_w, bound_w,
+                                 [_host_vector(ks, templates_w[t], slots, bits) for t in range(templates_w.shape[0])],
+                                 slots, bits)
 
 
 def gather_match_bits(dist, world: int, device, torch, local_out: np.ndarray) -> np.ndarray:

@@ -748,6 +748,39 @@ void tfhe_random_generator_setSeed(uint32_t* values, int32_t size) {
 }
 
 // ------------------------------------------------------------------------------------------------ extensions
+// Synthetic inputs generated on the device: arrays[k][i] <- fresh encryption of
+// bits[k*nbelems + i], one kernel launch for the whole list, without the 2.5 KB per bit crossing PCIe.  With a test
+// backend installed the words are made on the host and uploaded instead.
+void peba1_encrypt_array_list_device(LweSample* const* arrays, int32_t narrays, int32_t nbelems, const int32_t* bits,
+                                     const TFheGateBootstrappingSecretKeySet* key, uint64_t seed) {
+    if (narrays <= 0 || nbelems <= 0) return;
+    if (!arrays || !bits || !key || !key->lwe_key) die("peba1_encrypt_array_list_device: bad arguments");
+    Engine* e = engine_of(&key->cloud);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const int64_t total = (int64_t)narrays * nbelems;
+    std::vector<int64_t> slots((size_t)total);
+    for (int32_t k = 0; k < narrays; ++k)
+        for (int32_t i = 0; i < nbelems; ++i) {
+            const int64_t id = new_wire(e, 0);  // the sample owns the only reference
+            slots[(size_t)k * nbelems + i] = g_wires[id].slot = alloc_slot(e);
+            sample_assign(&arrays[k][i], (Handle)id << 1);
+        }
+    ensure_capacity(e);
+    if (e->tb) {
+        std::vector<int32_t> w((size_t)total * (size_t)e->words);
+        peba1_encrypt_bits(key, bits, total, seed, w.data());
+        CUCHK(e, be_upload_slots(e, slots.data(), total, w.data()));
+    } else {
+        CUCHK(e, peba1_cuda_encrypt_bits(e->ctx, key->lwe_key, bits, slots.data(), 0, total, 0, seed,
+                                         key->params->ks_stdev));
+    }
+    g_stats.device_encryptions += (uint64_t)total;
+}
+void peba1_encrypt_array_device(LweSample* array, int32_t nbelems, const int32_t* bits,
+                                const TFheGateBootstrappingSecretKeySet* key, uint64_t seed) {
+    peba1_encrypt_array_list_device(&array, 1, nbelems, bits, key, seed);
+}
+
 void peba1_host_set_device(int device) { g_device = device; }
 void peba1_host_set_test_backend(const peba1_test_backend* backend) { g_test_backend = backend; }
 void peba1_flush(void) {

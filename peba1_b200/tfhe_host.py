@@ -38,7 +38,7 @@ class HostStats(C.Structure):
                 ("flushes", C.c_uint64), ("max_level_width", C.c_uint64), ("uploads", C.c_uint64),
                 ("downloads", C.c_uint64), ("live_slots", C.c_uint64), ("peak_slots", C.c_uint64),
                 ("flush_seconds", C.c_double), ("executed_gates", C.c_uint64), ("executed_pbs", C.c_uint64),
-                ("folded", C.c_uint64), ("dead", C.c_uint64)]
+                ("folded", C.c_uint64), ("dead", C.c_uint64), ("device_encryptions", C.c_uint64)]
 
 
 class TestBackend(C.Structure):
@@ -106,6 +106,8 @@ def load_library():
     L.peba1_keyset_ksk.argtypes = [CK]
     L.peba1_encrypt_bits.argtypes = [SK, i32p, C.c_int64, C.c_uint64, i32p]
     L.peba1_decrypt_words.argtypes = [SK, i32p, C.c_int64, i32p]
+    L.peba1_encrypt_array_device.argtypes = [LS, C.c_int32, i32p, SK, C.c_uint64]
+    L.peba1_encrypt_array_list_device.argtypes = [C.POINTER(LS), C.c_int32, C.c_int32, i32p, SK, C.c_uint64]
     L.peba1_cuda_context_of.restype = C.c_void_p
     L.peba1_cuda_context_of.argtypes = [CK]
     L.peba1_math_add.argtypes = [LS, LS, LS, LS, C.c_int, CK]
@@ -188,6 +190,18 @@ class KeySet:
         words = np.ascontiguousarray(words, dtype=np.int32).reshape(-1, self.words)
         for i in range(words.shape[0]):
             self.L.peba1_sample_set(self.at(arr, i), _i32(words[i]))
+
+    def encrypt_array_device(self, arr, bits, seed: int):
+        """arr[i] <- fresh encryption of bits[i], generated on the GPU (no host->device ciphertext traffic)."""
+        bits = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)
+        self.L.peba1_encrypt_array_device(arr, bits.size, _i32(bits), self.sk, seed)
+
+    def encrypt_array_list_device(self, arrs, nbelems: int, bits, seed: int):
+        """arrs[k][i] <- fresh encryption of bits[k*nbelems + i], one launch for the whole list."""
+        bits = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)
+        assert bits.size == len(arrs) * nbelems
+        ptrs = (C.POINTER(LweSample) * len(arrs))(*arrs)
+        self.L.peba1_encrypt_array_list_device(ptrs, len(arrs), nbelems, _i32(bits), self.sk, seed)
 
     def get_words(self, arr, count: int) -> np.ndarray:
         out = np.empty((count, self.words), dtype=np.int32)

@@ -343,3 +343,40 @@ def test_fold_mode_face_match_size(env):
     L.peba1_set_mode(0)
     print("PBS and levels per face match by mode:", counts)
     assert counts[0][0] == 215544 and counts[1][0] < 0.6 * counts[0][0] and counts[2][0] < counts[1][0]
+
+
+def test_encrypt_array_on_device_path(env):
+    """peba1_encrypt_array_device: the samples become pool-resident wires holding fresh encryptions of
+    the given bits; usable as gate operands.  (On the simulator the words are made on the host; the kernel itself is
+    checked by the -m gpu test.)"""
+    L, ks, sim = env
+    bits = np.random.default_rng(5).integers(0, 2, size=24)
+    arr = ks.new_array(24)
+    s0 = ks.stats()
+    ks.encrypt_array_device(arr, bits, seed=99)
+    assert ks.stats().device_encryptions - s0.device_encryptions == 24
+    assert ks.decrypt(ks.get_words(arr, 24)).tolist() == bits.tolist()
+    out = ks.new_array(1)
+    L.bootsXOR(out, ks.at(arr, 0), ks.at(arr, 1), ks.cloud)
+    assert int(ks.decrypt(ks.get_words(out, 1))[0]) == int(bits[0] ^ bits[1])
+    ks.free_array(24, arr)
+    ks.free_array(1, out)
+
+
+def test_gallery_shards_and_device_generated_templates(env):
+    """BASELINE configs[4] plumbing: every rank derives its own shard of the synthetic gallery (template t is a function
+    of (seed, t) only), encrypts it where it is used, and Function_f on those arrays gives the expected match bits."""
+    from peba1_b200 import gallery as G
+    L, ks, sim = env
+    total = 37
+    whole = G.synthetic_gallery_shard(total, 0, total, slots=4)
+    parts = [G.synthetic_gallery_shard(total, *G.shard_bounds(total, 3, r), slots=4) for r in range(3)]
+    assert np.array_equal(np.concatenate([p[1] for p in parts]), whole[1])
+    assert np.array_equal(np.concatenate([p[2] for p in parts]), whole[2])
+    assert all(np.array_equal(p[0], whole[0]) for p in parts)
+    assert 0 < int((whole[2] == 0).sum()) < total                 # planted near-copies match, random templates do not
+    probe, gal, expect = G.synthetic_gallery_shard(total, 0, 3, slots=4)
+    tv = G.encrypt_templates_on_device(ks, gal, bits=8, seed=5)
+    out = G.match_template_arrays(ks, ks.encrypt(G.bits_of(probe, 8), 1), ks.encrypt(G.bits_of([512], 24), 2), tv,
+                                  slots=4, bits=8)
+    assert ks.decrypt(out).tolist() == expect.tolist()

@@ -193,3 +193,32 @@ def test_kernel_variants_agree(engine, keys):
         engine.set_option("tm_teams", 0)
         engine.set_option("ks_group", 1)
         engine.set_option("pair_min_batch", -1)
+
+
+@pytest.mark.gpu
+def test_device_side_encryption(engine, keys):
+    """peba1_cuda_encrypt_bits: decrypts to the bits, noise of the stated width, uniform masks,
+    a function of (seed, index) only."""
+    n = 4096
+    bits = np.random.default_rng(3).integers(0, 2, size=n)
+    engine.reserve(3 * n)
+    engine.encrypt_bits(keys.lwe_key, bits, 0, seed=1234)
+    ct = engine.download(0, n)
+    assert np.array_equal(keys.decrypt(ct), bits)
+    ph = keys.phase(ct).astype(np.int64)                         # torus32 phase = +-2^29 + noise
+    noise = (ph - np.where(bits == 1, 1 << 29, -(1 << 29))).astype(np.float64) / 2.0**32
+    assert abs(noise.std() / 2.0**-15 - 1.0) < 0.1 and abs(noise.mean()) < 2.0**-15 * 0.1
+    mask = ct[:, :-1].astype(np.uint32)
+    assert abs((mask >> 31).mean() - 0.5) < 0.002 and abs((mask & 1).mean() - 0.5) < 0.002
+    assert len(np.unique(mask[:, 0])) > n - 4
+    # same (seed, index) -> same ciphertext, whatever the slot and the launch shape
+    engine.encrypt_bits(keys.lwe_key, bits[100:200], 2 * n, seed=1234, index0=100)
+    assert np.array_equal(engine.download(2 * n, 100), ct[100:200])
+    slots = n + np.arange(50)[::-1]
+    engine.encrypt_bits(keys.lwe_key, bits[:50], 0, seed=1234, slots=slots)
+    assert np.array_equal(engine.download_slots(slots), ct[:50])
+    engine.encrypt_bits(keys.lwe_key, bits[:8], 2 * n, seed=1235)
+    assert not np.array_equal(engine.download(2 * n, 8), ct[:8])
+    # fresh encryptions are valid gate inputs
+    out = engine.gate_batch_host("NAND", ct[:64], ct[64:128])
+    assert np.array_equal(keys.decrypt(out), 1 - (bits[:64] & bits[64:128]))
