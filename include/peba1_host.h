@@ -67,6 +67,7 @@ void peba1_reset_stats(void);
 /* Raw sample access (n+1 words: a[0..n-1], b).  _get flushes if the value is still pending. */
 int32_t peba1_sample_words(const TFheGateBootstrappingParameterSet* params);
 void peba1_sample_get(const LweSample* sample, const TFheGateBootstrappingCloudKeySet* bk, int32_t* words);
+void peba1_sample_get_words(const LweSample* sample, int32_t* words); /* as _get, without naming the key */
 void peba1_sample_set(LweSample* sample, const int32_t* words);
 LweSample* peba1_sample_at(LweSample* array, int32_t index); /* &array[index] for bindings */
 
@@ -76,6 +77,9 @@ TFheGateBootstrappingSecretKeySet* peba1_new_secret_keyset_seeded(const TFheGate
 TFheGateBootstrappingSecretKeySet* peba1_new_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params,
                                                                 const int32_t* lwe_key, const int32_t* tlwe_key,
                                                                 const int32_t* bk, const int32_t* ksk);
+/* A stand-alone cloud keyset (what a server holds); free it with delete_gate_bootstrapping_cloud_keyset. */
+TFheGateBootstrappingCloudKeySet* peba1_new_cloud_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params,
+                                                                     const int32_t* bk, const int32_t* ksk);
 /* Multi-GPU replicas: a keyset with no key material.  Its GPU context is created without keys; the caller fills the
    device key buffers (peba1_cuda_key_device_buffers on peba1_cuda_context_of) with an NCCL broadcast from the rank that
    holds the real keys, then calls peba1_cuda_keys_mark_loaded.  It cannot encrypt or decrypt. */

@@ -40,6 +40,7 @@ struct peba1_key_material {
     TFheGateBootstrappingParameterSet params;
     std::vector<int32_t> lwe_key, tlwe_key, bk, ksk;
     peba1::Engine* engine = nullptr;
+    TFheGateBootstrappingSecretKeySet* cloud_only_owner = nullptr;  // set for a cloud keyset loaded from a file
 };
 
 namespace peba1 {
@@ -648,7 +649,21 @@ void delete_gate_bootstrapping_secret_keyset(TFheGateBootstrappingSecretKeySet* 
     km->ksk.clear(); km->ksk.shrink_to_fit();
     delete keyset;
 }
-void delete_gate_bootstrapping_cloud_keyset(TFheGateBootstrappingCloudKeySet*) {}
+// A cloud keyset is normally embedded in its secret keyset (src/main.cpp:23 takes its address; :601 is commented out), so
+// there is nothing to free — except for one loaded from a file (tfhe_io), which owns a key-less wrapper.
+void delete_gate_bootstrapping_cloud_keyset(TFheGateBootstrappingCloudKeySet* cloud) {
+    if (cloud && cloud->material && cloud->material->cloud_only_owner &&
+        &cloud->material->cloud_only_owner->cloud == cloud)
+        delete_gate_bootstrapping_secret_keyset(cloud->material->cloud_only_owner);
+}
+TFheGateBootstrappingCloudKeySet* peba1_new_cloud_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params,
+                                                                     const int32_t* bk, const int32_t* ksk) {
+    TFheGateBootstrappingSecretKeySet* ks = peba1_new_keyset_from_arrays(params, nullptr, nullptr, bk, ksk);
+    ks->cloud.material->cloud_only_owner = ks;
+    ks->lwe_key = nullptr;   // a cloud keyset cannot encrypt or decrypt
+    ks->tlwe_key = nullptr;
+    return &ks->cloud;
+}
 
 LweSample* new_gate_bootstrapping_ciphertext_array(int32_t nbelems, const TFheGateBootstrappingParameterSet* params) {
     if (nbelems < 0 || !params) die("bad ciphertext array request");
@@ -828,6 +843,24 @@ void peba1_sample_get(const LweSample* sample, const TFheGateBootstrappingCloudK
         return;
     }
     fetch(engine_of(bk), h, words);
+}
+void peba1_sample_get_words(const LweSample* sample, int32_t* words) {
+    const int n = sample->peba1_n;
+    const Handle h = sample->peba1_handle;
+    if (h == 0) {
+        memcpy(words, sample->a, sizeof(int32_t) * (size_t)n);
+        words[n] = sample->b;
+    } else if (is_const(h)) {
+        memset(words, 0, sizeof(int32_t) * (size_t)n);
+        words[n] = (h & 1) ? (1 << 29) : -(1 << 29);
+    } else {
+        Engine* e;
+        {
+            std::lock_guard<std::recursive_mutex> lk(g_mu);
+            e = g_engines[g_wires[h >> 1].eng];
+        }
+        fetch(e, h, words);
+    }
 }
 void peba1_sample_set(LweSample* sample, const int32_t* words) {
     // words: a[0..n-1], b

@@ -108,6 +108,23 @@ def load_library():
     L.peba1_decrypt_words.argtypes = [SK, i32p, C.c_int64, i32p]
     L.peba1_encrypt_array_device.argtypes = [LS, C.c_int32, i32p, SK, C.c_uint64]
     L.peba1_encrypt_array_list_device.argtypes = [C.POINTER(LS), C.c_int32, C.c_int32, i32p, SK, C.c_uint64]
+    # <tfhe/tfhe_io.h>: FILE* arguments are libc streams (see open_file below)
+    FP = C.c_void_p
+    L.export_tfheGateBootstrappingParameterSet_toFile.argtypes = [FP, PS]
+    L.new_tfheGateBootstrappingParameterSet_fromFile.restype = PS
+    L.new_tfheGateBootstrappingParameterSet_fromFile.argtypes = [FP]
+    L.export_tfheGateBootstrappingCloudKeySet_toFile.argtypes = [FP, CK]
+    L.new_tfheGateBootstrappingCloudKeySet_fromFile.restype = CK
+    L.new_tfheGateBootstrappingCloudKeySet_fromFile.argtypes = [FP]
+    L.export_tfheGateBootstrappingSecretKeySet_toFile.argtypes = [FP, SK]
+    L.new_tfheGateBootstrappingSecretKeySet_fromFile.restype = SK
+    L.new_tfheGateBootstrappingSecretKeySet_fromFile.argtypes = [FP]
+    L.export_gate_bootstrapping_ciphertext_toFile.argtypes = [FP, LS, PS]
+    L.import_gate_bootstrapping_ciphertext_fromFile.argtypes = [FP, LS, PS]
+    L.delete_gate_bootstrapping_cloud_keyset.argtypes = [CK]
+    L.peba1_sample_get_words.argtypes = [LS, i32p]
+    L.peba1_new_cloud_keyset_from_arrays.restype = CK
+    L.peba1_new_cloud_keyset_from_arrays.argtypes = [PS, i32p, i32p]
     L.peba1_cuda_context_of.restype = C.c_void_p
     L.peba1_cuda_context_of.argtypes = [CK]
     L.peba1_math_add.argtypes = [LS, LS, LS, LS, C.c_int, CK]
@@ -223,3 +240,25 @@ class KeySet:
         s = HostStats()
         self.L.peba1_get_stats(C.byref(s))
         return s
+
+
+class open_file:
+    """libc FILE* for the <tfhe/tfhe_io.h> functions: `with open_file(path, "wb") as F: L.export_...(F, ...)`."""
+    _libc = None
+
+    def __init__(self, path: str, mode: str):
+        if open_file._libc is None:
+            open_file._libc = C.CDLL(None)
+            open_file._libc.fopen.restype = C.c_void_p
+            open_file._libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+            open_file._libc.fclose.argtypes = [C.c_void_p]
+        self.fp = open_file._libc.fopen(os.fsencode(path), mode.encode())
+        if not self.fp:
+            raise OSError(f"cannot open {path!r} with mode {mode!r}")
+
+    def __enter__(self):
+        return self.fp
+
+    def __exit__(self, *exc):
+        open_file._libc.fclose(self.fp)
+        return False

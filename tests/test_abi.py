@@ -62,3 +62,27 @@ def test_product_never_imports_oracle():
                     continue
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "tfhe_oracle" not in txt and "pyoracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_host_library_exports_every_declared_function():
+    """libpeba1_tfhe.so defines every function the TFHE-compatible headers, Math.h mirror and host extensions declare
+    (C symbols by name; the C++ entry points of peba1_math.h — std::vector arguments like the reference's — mangled)."""
+    import subprocess
+    from peba1_b200 import tfhe_host as H
+    H.load_library()
+    nm = subprocess.run(["nm", "-D", "--defined-only", H.lib_path()], capture_output=True, text=True, check=True).stdout
+    exported = [ln.split()[-1] for ln in nm.splitlines() if ln.strip()]
+    inc = os.path.join(ROOT, "include")
+    headers = [os.path.join(inc, "peba1_host.h"), os.path.join(inc, "peba1_math.h")] + \
+              [os.path.join(inc, "tfhe", f) for f in sorted(os.listdir(os.path.join(inc, "tfhe")))]
+    pat = re.compile(r"\b((?:boots|peba1_|new_|delete_|export_|import_|tfhe_random_|HE_|Function_|compare_bit|minimum)"
+                     r"[A-Za-z0-9_]*)\s*\(")
+    declared = set()
+    for h in headers:
+        src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        declared |= set(pat.findall(src))
+    declared = {d for d in declared if not d.startswith("peba1_cuda_")}   # libpeba1_cuda's, checked above
+    assert len(declared) > 60
+    missing = [d for d in sorted(declared) if d not in exported and not any(d in e for e in exported if e.startswith("_Z"))]
+    assert not missing, missing
