@@ -138,6 +138,47 @@ def match_templates(ks: "H.KeySet", probe_w, bound_w, templates_w, slots: int = 
                                  slots, bits)
 
 
+def authenticate_batch(ks: "H.KeySet", probe_vecs, template_vecs, bound_w, r0_w, r1_w, slots: int = 128, bits: int = 8):
+    """The PEBA1 protocol step of the server (src/main.cpp:534-570) for MANY clients at once:
+    client k sent its encrypted probe and two encrypted random bytes r0_k, r1_k; the server holds the client's enrolled
+    template.  For every k: b_k = Function_f(probe_k, template_k, bound) (1 iff squared distance > bound, quirk Q3), then
+    y_k = Function_g(b_k, r0_k, r1_k) = r1_k if b_k else (-r0_k mod 256) (quirks Q1/Q4).  All K instances are recorded
+    into one batch, so each circuit level of f (377) and g (116) is ONE launch pair whatever K is.
+    probe_vecs / template_vecs: K vectors as made by _host_vector / encrypt_templates_on_device (freed here);
+    r0_w, r1_w: [K, bits, words] ciphertext words.  Returns y as [K, bits, words]."""
+    L = H.load_library()
+    K = len(probe_vecs)
+    assert len(template_vecs) == K and r0_w.shape[0] == K and r1_w.shape[0] == K
+    eb = ks.new_array(24)
+    ks.set_words(eb, bound_w)
+    rb = [ks.new_array(24) for _ in range(K)]
+    ys = [ks.new_array(bits + 1) for _ in range(K)]
+    rs = []
+    for k in range(K):
+        e0, e1 = ks.new_array(bits), ks.new_array(bits)
+        ks.set_words(e0, r0_w[k])
+        ks.set_words(e1, r1_w[k])
+        rs.append((e0, e1))
+    L.peba1_batch_begin()
+    for k in range(K):
+        L.peba1_math_function_f(rb[k], probe_vecs[k][1], template_vecs[k][1], slots, eb, bits, ks.cloud)
+    for k in range(K):
+        L.peba1_math_function_g(ys[k], rb[k], rs[k][0], rs[k][1], bits, ks.cloud)
+    L.peba1_batch_end()
+    out = np.stack([ks.get_words(ys[k], bits) for k in range(K)]) if K else np.zeros((0, bits, ks.words), np.int32)
+    for arrs, _ in list(probe_vecs) + list(template_vecs):
+        for a in arrs:
+            ks.free_array(bits, a)
+    for e0, e1 in rs:
+        ks.free_array(bits, e0)
+        ks.free_array(bits, e1)
+    for a in rb + [eb]:
+        ks.free_array(24, a)
+    for a in ys:
+        ks.free_array(bits + 1, a)
+    return out
+
+
 def gather_match_bits(dist, world: int, device, torch, local_out: np.ndarray) -> np.ndarray:
     """All-gather of the encrypted match bits; returns [world*T, words] (rank-major) on every rank."""
     t = torch.from_numpy(np.ascontiguousarray(local_out)).to(device)

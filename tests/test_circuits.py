@@ -380,3 +380,32 @@ def test_gallery_shards_and_device_generated_templates(env):
     out = G.match_template_arrays(ks, ks.encrypt(G.bits_of(probe, 8), 1), ks.encrypt(G.bits_of([512], 24), 2), tv,
                                   slots=4, bits=8)
     assert ks.decrypt(out).tolist() == expect.tolist()
+
+
+def test_batched_authentication_service(env):
+    """the server side of the protocol (main.cpp:534-570) for several clients in one batch.  y = r1
+    iff the client's probe is FARTHER than the bound from its template (the reference's polarity, Q3), else -r0 mod 256
+    (Q1); the batch shares every circuit level: as many launches as ONE client needs."""
+    from peba1_b200 import gallery as G
+    L, ks, sim = env
+    rng = np.random.default_rng(8)
+    K, slots, bound = 3, 4, 35
+    tmpl = rng.integers(1, 200, size=(K, slots))
+    probes = tmpl + np.array([[1], [3], [4]])            # squared distances 4, 36, 64
+    r0, r1 = rng.integers(1, 256, size=K), rng.integers(0, 256, size=K)
+    pv = [G._host_vector(ks, ks.encrypt(G.bits_of(probes[k], 8), 100 + k), slots, 8) for k in range(K)]
+    tv = G.encrypt_templates_on_device(ks, tmpl, bits=8, seed=9)
+    r0w = np.stack([ks.encrypt(G.bits_of([r0[k]], 8), 200 + k) for k in range(K)])
+    r1w = np.stack([ks.encrypt(G.bits_of([r1[k]], 8), 300 + k) for k in range(K)])
+    sim.reset_schedule()
+    y = G.authenticate_batch(ks, pv, tv, ks.encrypt(G.bits_of([bound], 24), 1), r0w, r1w, slots=slots, bits=8)
+    got = [int(sum(int(b) << i for i, b in enumerate(ks.decrypt(y[k])))) for k in range(K)]
+    far = ((probes - tmpl) ** 2).sum(axis=1) > bound
+    assert got == [int(r1[k]) if far[k] else int((-r0[k]) % 256) for k in range(K)]
+    levels_batch = len(sim.level_widths)
+    # one client alone needs the same number of levels
+    pv1 = [G._host_vector(ks, ks.encrypt(G.bits_of(probes[0], 8), 100), slots, 8)]
+    tv1 = G.encrypt_templates_on_device(ks, tmpl[:1], bits=8, seed=9)
+    sim.reset_schedule()
+    G.authenticate_batch(ks, pv1, tv1, ks.encrypt(G.bits_of([bound], 24), 1), r0w[:1], r1w[:1], slots=slots, bits=8)
+    assert len(sim.level_widths) == levels_batch

@@ -228,3 +228,27 @@ def test_config3_multiplier16_instances(gpu_keys):
         assert gpu_keys.decrypt_int(R[i], 47) == int(xs[i]) * int(ys[i])
     for i in range(n):
         gpu_keys.free_array(16, A[i]); gpu_keys.free_array(16, B[i]); gpu_keys.free_array(47, R[i])
+
+
+def test_batched_authentication_with_device_generated_templates(gpu_keys):
+    """SURVEY §8f items 2 + 4 on the GPU: enrolled templates encrypted on the device, three clients authenticated in one
+    batch (Function_f then Function_g per client, levels shared); decrypted verdicts follow main.cpp:578 with the
+    reference's polarity and quirks."""
+    from peba1_b200 import gallery as G
+    ks = gpu_keys
+    rng = np.random.default_rng(8)
+    K, slots, bound = 3, 8, 120
+    tmpl = rng.integers(1, 200, size=(K, slots))
+    probes = tmpl + np.array([[1], [4], [5]])            # squared distances 8, 128, 200
+    r0, r1 = rng.integers(1, 256, size=K), rng.integers(0, 256, size=K)
+    pv = [G._host_vector(ks, ks.encrypt(G.bits_of(probes[k], 8), 100 + k), slots, 8) for k in range(K)]
+    s0 = ks.stats()
+    tv = G.encrypt_templates_on_device(ks, tmpl, bits=8, seed=9)
+    assert ks.stats().device_encryptions - s0.device_encryptions == K * slots * 8
+    r0w = np.stack([ks.encrypt(G.bits_of([r0[k]], 8), 200 + k) for k in range(K)])
+    r1w = np.stack([ks.encrypt(G.bits_of([r1[k]], 8), 300 + k) for k in range(K)])
+    y = G.authenticate_batch(ks, pv, tv, ks.encrypt(G.bits_of([bound], 24), 1), r0w, r1w, slots=slots, bits=8)
+    got = [int(sum(int(b) << i for i, b in enumerate(ks.decrypt(y[k])))) for k in range(K)]
+    far = ((probes - tmpl) ** 2).sum(axis=1) > bound
+    assert far.tolist() == [False, True, True]
+    assert got == [int(r1[k]) if far[k] else int((-r0[k]) % 256) for k in range(K)]
