@@ -31,12 +31,32 @@ constexpr int kTmBk = 336;      // shared-key variant: 2 row buffers x 64 cells,
 // Shared memory of one team in this version: ONE cross-team exchange buffer (two barriers per transform instead of
 // double buffering) so that 8 teams fit: 8 KB + 8 KB + 8 KB + 1.25 KB = 25.25 KB per team.
 struct __align__(16) TeamSmemTm {
+    static constexpr bool kAliased = false;
+    static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;  // tensor-memory columns (8 teams: 4 x 64 sums)
     double2  ex1[kM];
     double2  ex2[kM];
     int32_t  acc[2][kN];
     uint16_t bara[640];
     unsigned long long ex1_free;  // mbarrier: "the cross-team exchange buffer may be overwritten" (2 arrivals, one per warp)
     unsigned long long pad_;
+    PEBA1_HD double2* e1() { return ex1; }
+    PEBA1_HD double2* e2() { return ex2; }
+};
+
+// The same with ONE exchange buffer: 17.3 KB per team instead of 25.3 KB, so 10 teams (20 warps, 96 registers) fit one SM
+// instead of 8.  The inner exchange may live in the cross-team buffer because thread (hi, lo) only ever touches region
+// [64 hi, 64 hi + 64) there, in both exchanges, and the eight threads of a region sit in one warp: the hazards between
+// the two uses are warp-local (__syncwarp), only the "buffer free" signal moves to after the LAST read of a transform.
+struct __align__(16) TeamSmemTm1 {
+    static constexpr bool kAliased = true;
+    static constexpr int kTw1 = 320, kTw2 = 352, kZero = 384;  // 10 teams: 5 x 64 columns of sums come first
+    double2  ex1[kM];
+    int32_t  acc[2][kN];
+    uint16_t bara[640];
+    unsigned long long ex1_free;
+    unsigned long long pad_;
+    PEBA1_HD double2* e1() { return ex1; }
+    PEBA1_HD double2* e2() { return ex1; }
 };
 
 PEBA1_HD double2 words_to_c(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -80,11 +100,13 @@ PEBA1_HD void tm_store8(Env& env, int col, const double2 (&v)[8]) {
 }
 
 // Forward transform; twiddles come from tensor memory right before their use.
-template <class Env>
-PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
+template <class Env, class SM>
+PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
     const int tid = env.tid;
+    double2* const ex1 = sm.e1();
+    double2* const ex2 = sm.e2();
     uint32_t w[32];
-    env.tmem_ld32(kTmTw1, w);  // in flight while the first pass computes
+    env.tmem_ld32(SM::kTw1, w);  // in flight while the first pass computes
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
     radix8<false>(x);
@@ -92,56 +114,62 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
     env.ex1_acquire();  // every reader of the previous transform's ex1 is done (split-phase: they signalled long ago)
 #pragma unroll
     for (int k0 = 0; k0 < 8; ++k0)
-        sm.ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
-    env.tmem_ld32(kTmTw2, w);  // in flight across the barrier, the loads and the second pass
+        ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
+    env.tmem_ld32(SM::kTw2, w);  // in flight across the barrier, the loads and the second pass
     env.team_sync();
     const int hi = tid >> 3, lo = tid & 7;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) x[b] = sm.ex1[64 * hi + 8 * b + lo];
-    env.ex1_release();
+    for (int b = 0; b < 8; ++b) x[b] = ex1[64 * hi + 8 * b + lo];
+    if (!SM::kAliased) env.ex1_release();
     radix8<false>(x);
     env.tmem_wait_ld();
 #if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 2  /* what-if build: no inner exchange in the forward transform */
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
 #else
-    sm.ex2[64 * hi + lo] = x[0];
+    if (SM::kAliased) env.warp_sync();  // the region's eight readers above are done before it is rewritten
+    ex2[64 * hi + lo] = x[0];
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1)
-        sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
+        ex2[64 * hi + 8 * k1 + (lo ^ k1)] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
     env.warp_sync();
 #pragma unroll
-    for (int c = 0; c < 8; ++c) x[c] = sm.ex2[64 * hi + 8 * lo + (c ^ lo)];
+    for (int c = 0; c < 8; ++c) x[c] = ex2[64 * hi + 8 * lo + (c ^ lo)];
 #endif
+    if (SM::kAliased) env.ex1_release();
     radix8<false>(x);
 }
 
-template <class Env>
-PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
+template <class Env, class SM>
+PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
     const int tid = env.tid;
     const int hi = tid >> 3, lo = tid & 7;
+    double2* const ex1 = sm.e1();
+    double2* const ex2 = sm.e2();
     uint32_t w[32];
-    env.tmem_ld32(kTmTw2, w);
+    env.tmem_ld32(SM::kTw2, w);
     radix8<true>(x);
     env.tmem_wait_ld();
-    env.warp_sync();  // previous readers of ex2 are done
-    sm.ex2[64 * hi + 8 * lo + lo] = x[0];
+    if (SM::kAliased) env.ex1_acquire();  // the previous transform's cross-team readers of this region are done
+    else env.warp_sync();                 // previous readers of ex2 are done
+    ex2[64 * hi + 8 * lo + lo] = x[0];
 #pragma unroll
     for (int c = 1; c < 8; ++c)
-        sm.ex2[64 * hi + 8 * lo + (c ^ lo)] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-    env.tmem_ld32(kTmTw1, w);
+        ex2[64 * hi + 8 * lo + (c ^ lo)] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+    env.tmem_ld32(SM::kTw1, w);
     env.warp_sync();
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) x[k1] = sm.ex2[64 * hi + 8 * k1 + (lo ^ k1)];
+    for (int k1 = 0; k1 < 8; ++k1) x[k1] = ex2[64 * hi + 8 * k1 + (lo ^ k1)];
     radix8<true>(x);
-    env.ex1_acquire();  // previous readers of ex1 are done
+    if (SM::kAliased) env.warp_sync();    // the region's readers above are done before it is rewritten
+    else env.ex1_acquire();               // previous readers of ex1 are done
 #pragma unroll
-    for (int b = 0; b < 8; ++b) sm.ex1[64 * hi + 8 * b + lo] = x[b];
+    for (int b = 0; b < 8; ++b) ex1[64 * hi + 8 * b + lo] = x[b];
     env.team_sync();
     env.tmem_wait_ld();
 #pragma unroll
     for (int k0 = 0; k0 < 8; ++k0)
-        x[k0] = cmul_conj(sm.ex1[64 * k0 + tid], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
+        x[k0] = cmul_conj(ex1[64 * k0 + tid], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
     env.ex1_release();
     radix8<true>(x);
 #pragma unroll
@@ -149,19 +177,19 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], TeamSmemTm& sm) {
 }
 
 // Writes this thread's twiddles into tensor memory (called once per kernel by the warps with warp/4 == 0).
-template <class Env>
+template <class SM = TeamSmemTm, class Env>
 PEBA1_HD void tm_store_twiddles(Env& env, const TeamTwiddles& tw) {
-    tm_store8(env, kTmTw1, tw.tw1);
-    tm_store8(env, kTmTw2, tw.tw2);
+    tm_store8(env, SM::kTw1, tw.tw1);
+    tm_store8(env, SM::kTw2, tw.tw2);
     uint32_t z[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) z[j] = 0u;
-    env.tmem_st16(kTmZero, z);
+    env.tmem_st16(SM::kZero, z);
     env.tmem_wait_st();
 }
 
-template <int L, int BGBIT, class Env>
-PEBA1_HD void blind_rotate_team_tm(Env& env, TeamSmemTm& sm, const double2* __restrict__ bkfft, int n,
+template <int L, int BGBIT, class Env, class SM>
+PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__ bkfft, int n,
                                    const int32_t* __restrict__ pool, int64_t pool_stride, PbsJob job,
                                    int32_t* __restrict__ u_out) {
     constexpr int ROWS = 2 * L;
@@ -195,11 +223,31 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, TeamSmemTm& sm, const double2* __re
     for (int i = 0; i < n; ++i) {
         const int abar = sm.bara[i];
         if (abar == 0) continue;
+#ifndef PEBA1_TV_IN_TMEM
         uint32_t tv[16];
+#endif
 #pragma unroll 1
         for (int r = 0; r < ROWS; ++r) {
             const int poly = r >= L ? 1 : 0;
             const int p = r - poly * L;
+#ifdef PEBA1_TV_IN_TMEM
+            // The rotated differences feed L digit levels.  Held in registers across the transforms they cost 16
+            // registers and push the kernel into spilling (LDL/STL = 6 % of its L1 wavefronts); parked in tensor
+            // memory between the levels they cost one store and L-1 loads per polynomial.
+            uint32_t tv[16];
+            if (p == 0) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
+                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
+                }
+                env.tmem_st16(env.tv_col, tv);
+            } else {
+                env.tmem_wait_st();
+                env.tmem_ld16(env.tv_col, tv);
+                env.tmem_wait_ld();
+            }
+#else
             if (p == 0) {
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
@@ -207,6 +255,7 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, TeamSmemTm& sm, const double2* __re
                     tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
                 }
             }
+#endif
             const int shift = 32 - (p + 1) * BGBIT;
             double2 x[8];
 #pragma unroll
@@ -224,7 +273,7 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, TeamSmemTm& sm, const double2* __re
             uint32_t w0[16], w1[16];
             double2 b0[4], b1[4];
             const int zsel = r > 0 ? 1 : 0;
-#define PEBA1_CHUNK_COL(q) (zsel ? sums + 32 * ((q) >> 1) + 16 * ((q) & 1) : kTmZero)
+#define PEBA1_CHUNK_COL(q) (zsel ? sums + 32 * ((q) >> 1) + 16 * ((q) & 1) : SM::kZero)
 #if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 1  /* what-if build (scripts/ablate.sh): no key loads */
 #define PEBA1_CHUNK_LDG(q, b)                                                                              \
     _Pragma("unroll") for (int e = 0; e < 4; ++e) b[e] = make_double2(1.0 + (q), 0.5 + e);

@@ -126,6 +126,7 @@ struct DevEnvTm {
     uint32_t group_mbar = 0;  // shared-key variant: smem address of the group's two mbarriers (one per row buffer)
     uint32_t ex1_mbar = 0;    // smem address of the team's "exchange buffer free" mbarrier
     uint32_t ex1_phase = 1;   // parity to wait for: the buffer starts free (the phase before the first counts as done)
+    int tv_col = 0;           // 16 tensor-memory columns where the decomposition input waits between digit levels
     // Split-phase write-after-read protection of the cross-team exchange buffer: a warp signals as soon as its reads
     // are done, the next writer waits just before writing, one whole transform pass later, so nobody actually blocks.
     __device__ __forceinline__ void ex1_release() const {
@@ -302,12 +303,15 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
 
 // K0+K1, tensor-memory version: 8 teams (512 threads, 16 warps) per CTA, one CTA per SM, <= 128 registers.
 constexpr int kTeamsTm = 8;
-template <int L, int BGBIT, int TEAMS>
+constexpr int kTeamsTm10 = 10;  // with the single-exchange-buffer layout (TeamSmemTm1): 20 warps, 96 registers
+template <int L, int BGBIT, int TEAMS, class SM = TeamSmemTm>
 __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     pbs_kernel_tm(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
-                  const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+                  const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out,
+                  unsigned long long* __restrict__ job_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TeamSmemTm* teams = reinterpret_cast<TeamSmemTm*>(smem_raw);
+    SM* teams = reinterpret_cast<SM*>(smem_raw);
+    __shared__ long long next_job[TEAMS];
     __shared__ uint32_t tm_alloc_base;
     const int warp = threadIdx.x >> 5;
     const int team = threadIdx.x / kTeam;
@@ -326,6 +330,7 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 64 * (warp >> 2),
                  tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16)};
     env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
+    env.tv_col = SM::kZero + 16 + 16 * (warp >> 2);
     if ((warp >> 2) == 0) {  // one warp per lane quarter publishes the per-thread twiddles
         TeamTwiddles tw;
 #pragma unroll
@@ -333,15 +338,30 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
             tw.tw1[j] = c_tables.tw1[env.tid][j];
             tw.tw2[j] = c_tables.tw2[env.tid & 7][j];
         }
-        tm_store_twiddles(env, tw);
+        tm_store_twiddles<SM>(env, tw);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t g = (int64_t)blockIdx.x * TEAMS + team;
-    if (g < count)
-        blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
-                                       u_out + g * (int64_t)kUStride);
+    if (job_counter == nullptr) {  // one job per team, fixed by the grid
+        const int64_t g = (int64_t)blockIdx.x * TEAMS + team;
+        if (g < count)
+            blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
+                                           u_out + g * (int64_t)kUStride);
+    } else {
+        // Persistent CTAs (one per SM): every team draws its next job from a global counter.  The bootstraps all take
+        // the same time, so this only matters at the end of a batch: instead of a last wave of whole CTAs on a few
+        // SMs, the remaining jobs spread over all SMs, whose teams run faster the fewer of them are left.
+        for (;;) {
+            if (env.tid == 0) next_job[team] = (long long)atomicAdd(job_counter, 1ULL);
+            env.team_sync();
+            const int64_t g = next_job[team];
+            env.team_sync();
+            if (g >= count) break;
+            blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
+                                           u_out + g * (int64_t)kUStride);
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -779,6 +799,7 @@ struct peba1_cuda_ctx {
     int64_t u_cap = 0;  // in samples
     void* d_jobs = nullptr;
     size_t d_jobs_cap = 0;
+    unsigned long long* d_job_counter = nullptr;  // persistent blind-rotation kernels draw job indices from it
     void* h_jobs = nullptr;  // pinned
     size_t h_jobs_cap = 0;
     int32_t* d_stage = nullptr;  // dense staging for uploads/downloads
@@ -865,7 +886,7 @@ int launch_pbs_tm_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
     const unsigned grid = (unsigned)((count + TEAMS - 1) / TEAMS);
     auto k = pbs_kernel_tm<L, BGBIT, TEAMS>;
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, TEAMS * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+    k<<<grid, TEAMS * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, nullptr);
     return 0;
 }
 
@@ -878,6 +899,35 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         auto k = pbs_kernel_tmsh<L, BGBIT>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+        return 0;
+    }
+    if ((c->kernel_variant == 5 || c->kernel_variant == 6) &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm10)) {
+        // 10 teams per CTA on the single-exchange-buffer layout; variant 6: persistent CTAs drawing jobs from a counter
+        const size_t smem = sizeof(TeamSmemTm1) * (size_t)kTeamsTm10;
+        unsigned grid = (unsigned)((count + kTeamsTm10 - 1) / kTeamsTm10);
+        unsigned long long* counter = nullptr;
+        if (c->kernel_variant == 6) {
+            if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+            CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+            counter = c->d_job_counter;
+            grid = std::min(grid, (unsigned)c->sm_count);
+        }
+        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm10, TeamSmemTm1>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm10 * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, counter);
+        return 0;
+    }
+    if (c->kernel_variant == 7 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
+        // the default 8-team kernel with persistent CTAs
+        const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
+        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+        const unsigned grid = std::min((unsigned)((count + kTeamsTm - 1) / kTeamsTm), (unsigned)c->sm_count);
+        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTm>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
         return 0;
     }
     if (c->kernel_variant == 4 &&
@@ -896,6 +946,17 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         auto k = pbs_kernel_pair<L, BGBIT, kTeamsPair>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, kTeamsPair * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
+        return 0;
+    }
+    if (c->kernel_variant == 1 && c->tm_teams == 0 && count >= (int64_t)c->sm_count * kTeamsTm) {
+        // wide batch (the default path): one persistent 8-team CTA per SM, jobs drawn from a counter (= variant 7)
+        const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
+        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTm>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(unsigned)c->sm_count, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u,
+                                                                     c->d_job_counter);
         return 0;
     }
     // Narrow levels (the long tail of a circuit: tens of gates per launch) cannot fill 148 SMs with 8 bootstraps per
@@ -1045,7 +1106,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
-    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 4 ? atoi(v) : 1;  // tuning aid
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 7 ? atoi(v) : 1;  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
@@ -1068,7 +1129,7 @@ int peba1_cuda_destroy(peba1_cuda_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->bkfft); cudaFree(c->ksk); cudaFree(c->pool); cudaFree(c->u); cudaFree(c->d_jobs); cudaFree(c->d_stage);
+    cudaFree(c->bkfft); cudaFree(c->ksk); cudaFree(c->pool); cudaFree(c->u); cudaFree(c->d_jobs); cudaFree(c->d_job_counter); cudaFree(c->d_stage);
     cudaFreeHost(c->h_jobs); cudaFreeHost(c->h_stage);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     cudaStreamDestroy(c->own_stream);
@@ -1528,7 +1589,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 4) return fail(PEBA1_EINVAL, "kernel_variant must be 0..4");
+        if (value < 0 || value > 7) return fail(PEBA1_EINVAL, "kernel_variant must be 0..7");
         c->kernel_variant = (int)value;
         return 0;
     }

@@ -181,6 +181,11 @@ def test_kernel_variants_agree(engine, keys):
         assert np.array_equal(engine.gate_batch_host("ANDYN", ca[:1], cb[:1]), want[:1]), "pair, single"
         engine.set_option("kernel_variant", 4)   # key rows through TMA + tcgen05.cp; 45 jobs: the last CTA has shadow teams
         assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), "tmk"
+        engine.set_option("kernel_variant", 5)   # 10 teams per CTA on one exchange buffer; 45 jobs: 4.5 CTAs
+        assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), "tm10"
+        for variant in (6, 7):                   # persistent CTAs drawing jobs from a counter (10 and 8 teams)
+            engine.set_option("kernel_variant", variant)
+            assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), variant
         engine.set_option("kernel_variant", 1)
         for teams in (1, 2, 4, 8):
             engine.set_option("tm_teams", teams)

@@ -69,3 +69,9 @@ def test_pair_variant_matches_exact_oracle(emu, oracle, keys):
                                             tin.ctypes.data_as(C.c_void_p), u4.ctypes.data_as(C.c_void_p),
                                             C.c_int64(3)) == 0
     assert np.array_equal(u4, u)
+    # one exchange buffer for both exchanges (TeamSmemTm1, the 10-teams-per-SM layout)
+    u5 = np.zeros((3, 1025), dtype=np.int32)
+    assert emu.peba1_emu_bootstrap_woks_tm1(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
+                                            tin.ctypes.data_as(C.c_void_p), u5.ctypes.data_as(C.c_void_p),
+                                            C.c_int64(3)) == 0
+    assert np.array_equal(u5, u)
