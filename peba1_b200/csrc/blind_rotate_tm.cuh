@@ -259,11 +259,8 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
             const int shift = 32 - (p + 1) * BGBIT;
             double2 x[8];
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                const int32_t dr = (int32_t)((tv[a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
-                const int32_t di = (int32_t)((tv[8 + a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
-                x[a] = make_double2(i2d(dr), i2d(di));
-            }
+            for (int a = 0; a < 8; ++a)
+                x[a] = make_double2(digit2d((tv[a] >> shift) & MASK_BG, HALF_BG), digit2d((tv[8 + a] >> shift) & MASK_BG, HALF_BG));
             team_fft_forward_tm(env, x, sm);
             // pointwise MAC against BK_i row r.  Accumulators live in tensor memory; chunk q = (column c, 4 bins).
             // Software pipeline: the accumulators and key values of chunk q+1 are in flight while chunk q is
