@@ -286,74 +286,6 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
         c_to_words(sacc, w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                               \
     }                                                                                                      \
     env.tmem_st16(sums + 32 * ((q) >> 1) + 16 * ((q) & 1), w);
-#if defined(PEBA1_MAC_E6)
-#define PEBA1_SCOL(q) (sums + 32 * ((q) >> 1) + 16 * ((q) & 1))
-#define PEBA1_MACONLY(q, w, b)                                                                             \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
-        double2 sacc = words_to_c(w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                      \
-        cfma(sacc, x[4 * ((q) & 1) + e], b[e]);                                                            \
-        c_to_words(sacc, w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                               \
-    }
-            env.tmem_ld16(PEBA1_CHUNK_COL(0), w0);
-            PEBA1_CHUNK_LDG(0, b0)
-            env.tmem_ld16(PEBA1_CHUNK_COL(1), w1);
-            PEBA1_CHUNK_LDG(1, b1)
-            env.tmem_wait_ld();
-            PEBA1_MACONLY(0, w0, b0)
-            env.tmem_stld16(PEBA1_SCOL(0), PEBA1_CHUNK_COL(2), w0);
-            PEBA1_CHUNK_LDG(2, b0)
-            PEBA1_MACONLY(1, w1, b1)
-            env.tmem_stld16(PEBA1_SCOL(1), PEBA1_CHUNK_COL(3), w1);
-            PEBA1_CHUNK_LDG(3, b1)
-            env.tmem_wait_ld();
-            PEBA1_MACONLY(2, w0, b0)
-            env.tmem_st16(PEBA1_SCOL(2), w0);
-            PEBA1_MACONLY(3, w1, b1)
-            env.tmem_st16(PEBA1_SCOL(3), w1);
-#undef PEBA1_SCOL
-#undef PEBA1_MACONLY
-#elif defined(PEBA1_MAC_E3)
-            for (int q = 0; q < 4; ++q) {
-                env.tmem_ld16(PEBA1_CHUNK_COL(q), w0);
-                PEBA1_CHUNK_LDG(q, b0)
-                env.tmem_wait_ld();
-                double2 sa[4];
-                _Pragma("unroll") for (int e = 0; e < 4; ++e) {
-                    sa[e] = words_to_c(w0[4 * e], w0[4 * e + 1], w0[4 * e + 2], w0[4 * e + 3]);
-                    cfma(sa[e], x[4 * (q & 1) + e], b0[e]);
-                }
-                _Pragma("unroll") for (int e = 0; e < 4; ++e) c_to_words(sa[e], w1[4 * e], w1[4 * e + 1], w1[4 * e + 2], w1[4 * e + 3]);
-                env.tmem_st16(sums + 32 * (q >> 1) + 16 * (q & 1), w1);
-            }
-#elif defined(PEBA1_MAC_X4)
-#define PEBA1_CHUNK_LD4(q, w) _Pragma("unroll") for (int e = 0; e < 4; ++e) env.tmem_ld4(PEBA1_CHUNK_COL(q) + (zsel ? 4 * e : 0), w[e]);
-#define PEBA1_CHUNK_MAC4(q, w, b)                                                                          \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
-        double2 sacc = words_to_c(w[e][0], w[e][1], w[e][2], w[e][3]);                                     \
-        cfma(sacc, x[4 * ((q) & 1) + e], b[e]);                                                            \
-        c_to_words(sacc, w[e][0], w[e][1], w[e][2], w[e][3]);                                              \
-        env.tmem_st4(sums + 32 * ((q) >> 1) + 16 * ((q) & 1) + 4 * e, w[e]);                               \
-    }
-            uint32_t v0[4][4], v1[4][4];
-            PEBA1_CHUNK_LD4(0, v0)
-            PEBA1_CHUNK_LDG(0, b0)
-            env.tmem_wait_ld();
-            PEBA1_CHUNK_LD4(1, v1)
-            PEBA1_CHUNK_LDG(1, b1)
-            PEBA1_CHUNK_MAC4(0, v0, b0)
-            env.tmem_wait_ld();
-            PEBA1_CHUNK_LD4(2, v0)
-            PEBA1_CHUNK_LDG(2, b0)
-            PEBA1_CHUNK_MAC4(1, v1, b1)
-            env.tmem_wait_ld();
-            PEBA1_CHUNK_LD4(3, v1)
-            PEBA1_CHUNK_LDG(3, b1)
-            PEBA1_CHUNK_MAC4(2, v0, b0)
-            env.tmem_wait_ld();
-            PEBA1_CHUNK_MAC4(3, v1, b1)
-#undef PEBA1_CHUNK_LD4
-#undef PEBA1_CHUNK_MAC4
-#else
             env.tmem_ld16(PEBA1_CHUNK_COL(0), w0);
             PEBA1_CHUNK_LDG(0, b0)
             env.tmem_wait_ld();
@@ -370,7 +302,6 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
             PEBA1_CHUNK_MAC(2, w0, b0)
             env.tmem_wait_ld();
             PEBA1_CHUNK_MAC(3, w1, b1)
-#endif
 #undef PEBA1_CHUNK_COL
 #undef PEBA1_CHUNK_LDG
 #undef PEBA1_CHUNK_MAC

@@ -90,6 +90,9 @@ PEBA1_HD double2 w32(int a) {
 }
 
 // X_k = sum_a x_a w^(a k), w = exp(+2 pi i/8) (INV: exp(-2 pi i/8)); in place, natural order in and out.
+// The odd half needs v1 * w and v3 * w^3 (w = (1 +- i)/sqrt2).  The factor 1/sqrt2 is not applied to v1 and v3 but
+// folded into the last butterfly as an FMA: x1,5 = p +- h s, x3,7 = q +- i h d with s, d built from v1 +- v3 by
+// additions only.  16 FP64 instructions for that half instead of 20 (52 per radix-8 instead of 56), one rounding less.
 template <bool INV>
 PEBA1_HD void radix8(double2 (&x)[8]) {
 #ifdef __CUDA_ARCH__
@@ -99,25 +102,32 @@ PEBA1_HD void radix8(double2 (&x)[8]) {
 #endif
     double2 u0 = cadd(x[0], x[4]), u1 = cadd(x[1], x[5]), u2 = cadd(x[2], x[6]), u3 = cadd(x[3], x[7]);
     double2 v0 = csub(x[0], x[4]), v1 = csub(x[1], x[5]), v2 = csub(x[2], x[6]), v3 = csub(x[3], x[7]);
-    if (!INV) {
-        v1 = make_double2((v1.x - v1.y) * h, (v1.x + v1.y) * h);    // * (1+i)/sqrt2
-        v2 = make_double2(-v2.y, v2.x);                              // * i
-        v3 = make_double2((-v3.x - v3.y) * h, (v3.x - v3.y) * h);    // * (-1+i)/sqrt2
-    } else {
-        v1 = make_double2((v1.x + v1.y) * h, (v1.y - v1.x) * h);    // * (1-i)/sqrt2
-        v2 = make_double2(v2.y, -v2.x);                              // * -i
-        v3 = make_double2((v3.y - v3.x) * h, (-v3.x - v3.y) * h);    // * (-1-i)/sqrt2
-    }
-    // two 4-point DFTs with w4 = +-i
+    // even half: a 4-point DFT of u with w4 = +-i
     {
         double2 p = cadd(u0, u2), q = csub(u0, u2), r = cadd(u1, u3), t = csub(u1, u3);
         double2 it = INV ? make_double2(t.y, -t.x) : make_double2(-t.y, t.x);
         x[0] = cadd(p, r); x[4] = csub(p, r); x[2] = cadd(q, it); x[6] = csub(q, it);
     }
+    // odd half
     {
-        double2 p = cadd(v0, v2), q = csub(v0, v2), r = cadd(v1, v3), t = csub(v1, v3);
-        double2 it = INV ? make_double2(t.y, -t.x) : make_double2(-t.y, t.x);
-        x[1] = cadd(p, r); x[5] = csub(p, r); x[3] = cadd(q, it); x[7] = csub(q, it);
+        v2 = INV ? make_double2(v2.y, -v2.x) : make_double2(-v2.y, v2.x);  // * +-i
+        const double2 p = cadd(v0, v2), q = csub(v0, v2);
+        const double2 m = csub(v1, v3), n = cadd(v1, v3);
+        if (!INV) {
+            // v1 (1+i) + v3 (-1+i) = (m.x - n.y, n.x + m.y) =: s;  v1 (1+i) - v3 (-1+i) = (n.x - m.y, m.x + n.y) =: d
+            const double2 sd = make_double2(m.x - n.y, n.x + m.y), dd = make_double2(n.x - m.y, m.x + n.y);
+            x[1] = make_double2(fma(h, sd.x, p.x), fma(h, sd.y, p.y));
+            x[5] = make_double2(fma(-h, sd.x, p.x), fma(-h, sd.y, p.y));
+            x[3] = make_double2(fma(-h, dd.y, q.x), fma(h, dd.x, q.y));   // q + i h d
+            x[7] = make_double2(fma(h, dd.y, q.x), fma(-h, dd.x, q.y));
+        } else {
+            // v1 (1-i) + v3 (-1-i) = (m.x + n.y, m.y - n.x) =: s;  v1 (1-i) - v3 (-1-i) = (n.x + m.y, n.y - m.x) =: d
+            const double2 sd = make_double2(m.x + n.y, m.y - n.x), dd = make_double2(n.x + m.y, n.y - m.x);
+            x[1] = make_double2(fma(h, sd.x, p.x), fma(h, sd.y, p.y));
+            x[5] = make_double2(fma(-h, sd.x, p.x), fma(-h, sd.y, p.y));
+            x[3] = make_double2(fma(h, dd.y, q.x), fma(-h, dd.x, q.y));   // q - i h d
+            x[7] = make_double2(fma(-h, dd.y, q.x), fma(h, dd.x, q.y));
+        }
     }
 }
 

@@ -800,8 +800,13 @@ struct peba1_cuda_ctx {
     void* d_jobs = nullptr;
     size_t d_jobs_cap = 0;
     unsigned long long* d_job_counter = nullptr;  // persistent blind-rotation kernels draw job indices from it
-    void* h_jobs = nullptr;  // pinned
-    size_t h_jobs_cap = 0;
+    // pinned job lists, double buffered: peba1_cuda_gates returns once its launches are queued, and only waits (on the
+    // copy event) before it overwrites the list it filled two chunks ago
+    void* h_jobs[2] = {nullptr, nullptr};
+    size_t h_jobs_cap[2] = {0, 0};
+    cudaEvent_t jobs_copied[2] = {nullptr, nullptr};
+    bool jobs_pending[2] = {false, false};
+    int jobs_next = 0;
     int32_t* d_stage = nullptr;  // dense staging for uploads/downloads
     size_t d_stage_cap = 0;
     int32_t* h_stage = nullptr;  // pinned
@@ -1130,7 +1135,11 @@ int peba1_cuda_destroy(peba1_cuda_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->bkfft); cudaFree(c->ksk); cudaFree(c->pool); cudaFree(c->u); cudaFree(c->d_jobs); cudaFree(c->d_job_counter); cudaFree(c->d_stage);
-    cudaFreeHost(c->h_jobs); cudaFreeHost(c->h_stage);
+    for (int b = 0; b < 2; ++b) {
+        cudaFreeHost(c->h_jobs[b]);
+        if (c->jobs_copied[b]) cudaEventDestroy(c->jobs_copied[b]);
+    }
+    cudaFreeHost(c->h_stage);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -1315,9 +1324,14 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
         }
         const size_t jb = (size_t)npbs * sizeof(PbsJob), kb = (size_t)m * sizeof(KsJob);
         const size_t kb_off = (jb + 255) / 256 * 256;
-        // a previous chunk may still be reading the pinned job list
-        if (done > 0) CU(cudaStreamSynchronize(c->stream));
-        if (int rc = ensure_pinned(&c->h_jobs, &c->h_jobs_cap, kb_off + kb)) return rc;
+        const int hb = c->jobs_next;
+        c->jobs_next ^= 1;
+        if (c->jobs_pending[hb]) {  // the copy that read this pinned list two chunks ago
+            CU(cudaEventSynchronize(c->jobs_copied[hb]));
+            c->jobs_pending[hb] = false;
+        }
+        if (!c->jobs_copied[hb]) CU(cudaEventCreateWithFlags(&c->jobs_copied[hb], cudaEventDisableTiming));
+        if (int rc = ensure_pinned(&c->h_jobs[hb], &c->h_jobs_cap[hb], kb_off + kb)) return rc;
         if (int rc = ensure_dev(&c->d_jobs, &c->d_jobs_cap, kb_off + kb)) return rc;
         if (c->u_cap < npbs) {
             if (c->u) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->u)); c->u = nullptr; c->u_cap = 0; }
@@ -1328,8 +1342,8 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
             }
             c->u_cap = want;
         }
-        PbsJob* pj = (PbsJob*)c->h_jobs;
-        KsJob* kj = (KsJob*)((char*)c->h_jobs + kb_off);
+        PbsJob* pj = (PbsJob*)c->h_jobs[hb];
+        KsJob* kj = (KsJob*)((char*)c->h_jobs[hb] + kb_off);
         int64_t ip = 0;
         for (int64_t i = 0; i < m; ++i) {
             const peba1_gate& g = gates[done + i];
@@ -1365,15 +1379,15 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
                 ip += 1;
             }
         }
-        CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, kb_off + kb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs[hb], kb_off + kb, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(c->jobs_copied[hb], c->stream));
+        c->jobs_pending[hb] = true;
         if (int rc = launch_pbs(c, c->pool, c->pool_stride, (const PbsJob*)c->d_jobs, npbs, c->u)) return rc;
         if (int rc = launch_ks(c, c->u, (const KsJob*)((char*)c->d_jobs + kb_off), m, c->pool)) return rc;
         if (int rc = collect_timing(c, true, true)) return rc;
         done += m;
     }
-    // the pinned job list is reused by the next call
-    CU(cudaStreamSynchronize(c->stream));
-    return 0;
+    return 0;  // asynchronous on the context stream (peba1_cuda_sync, or any download, waits)
 }
 
 int peba1_cuda_gate_batch(peba1_cuda_ctx* c, int32_t op, const int64_t* in0, const int64_t* in1, const int64_t* in2, const int64_t* out, int64_t count) {
