@@ -31,7 +31,7 @@ constexpr int kTmBk = 336;      // shared-key variant: 2 row buffers x 64 cells,
 // Shared memory of one team in this version: ONE cross-team exchange buffer (two barriers per transform instead of
 // double buffering) so that 8 teams fit: 8 KB + 8 KB + 8 KB + 1.25 KB = 25.25 KB per team.
 struct __align__(16) TeamSmemTm {
-    static constexpr bool kAliased = false;
+    static constexpr bool kAliased = false, kDouble = false;
     static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;  // tensor-memory columns (8 teams: 4 x 64 sums)
     double2  ex1[kM];
     double2  ex2[kM];
@@ -39,8 +39,8 @@ struct __align__(16) TeamSmemTm {
     uint16_t bara[640];
     unsigned long long ex1_free;  // mbarrier: "the cross-team exchange buffer may be overwritten" (2 arrivals, one per warp)
     unsigned long long pad_;
-    PEBA1_HD double2* e1() { return ex1; }
-    PEBA1_HD double2* e2() { return ex2; }
+    PEBA1_HD double2* e1(int) { return ex1; }
+    PEBA1_HD double2* e2(int) { return ex2; }
 };
 
 // The same with ONE exchange buffer: 17.3 KB per team instead of 25.3 KB, so 10 teams (20 warps, 96 registers) fit one SM
@@ -48,15 +48,31 @@ struct __align__(16) TeamSmemTm {
 // [64 hi, 64 hi + 64) there, in both exchanges, and the eight threads of a region sit in one warp: the hazards between
 // the two uses are warp-local (__syncwarp), only the "buffer free" signal moves to after the LAST read of a transform.
 struct __align__(16) TeamSmemTm1 {
-    static constexpr bool kAliased = true;
+    static constexpr bool kAliased = true, kDouble = false;
     static constexpr int kTw1 = 320, kTw2 = 352, kZero = 384;  // 10 teams: 5 x 64 columns of sums come first
     double2  ex1[kM];
     int32_t  acc[2][kN];
     uint16_t bara[640];
     unsigned long long ex1_free;
     unsigned long long pad_;
-    PEBA1_HD double2* e1() { return ex1; }
-    PEBA1_HD double2* e2() { return ex1; }
+    PEBA1_HD double2* e1(int) { return ex1; }
+    PEBA1_HD double2* e2(int) { return ex1; }
+};
+
+// Both exchanges of a transform in one buffer (as TeamSmemTm1), and TWO such buffers used alternately by successive
+// transforms: 25.3 KB per team like TeamSmemTm, but no "buffer free" mbarrier at all.  A buffer is rewritten two
+// transforms after it was read, and the team barrier of the transform in between separates the two: a thread passes that
+// barrier only when every thread of the team has arrived at it, i.e. has finished the reads of the transform before.
+struct __align__(16) TeamSmemTm2 {
+    static constexpr bool kAliased = true, kDouble = true;
+    static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;
+    double2  ex[2][kM];
+    int32_t  acc[2][kN];
+    uint16_t bara[640];
+    unsigned long long ex1_free;  // unused (kept so that the kernel's set-up code is the same for all layouts)
+    unsigned long long pad_;
+    PEBA1_HD double2* e1(int par) { return ex[par]; }
+    PEBA1_HD double2* e2(int par) { return ex[par]; }
 };
 
 PEBA1_HD double2 words_to_c(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -103,15 +119,16 @@ PEBA1_HD void tm_store8(Env& env, int col, const double2 (&v)[8]) {
 template <class Env, class SM>
 PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
     const int tid = env.tid;
-    double2* const ex1 = sm.e1();
-    double2* const ex2 = sm.e2();
+    const int par = SM::kDouble ? env.flip() : 0;
+    double2* const ex1 = sm.e1(par);
+    double2* const ex2 = sm.e2(par);
     uint32_t w[32];
     env.tmem_ld32(SM::kTw1, w);  // in flight while the first pass computes
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
     radix8<false>(x);
     env.tmem_wait_ld();
-    env.ex1_acquire();  // every reader of the previous transform's ex1 is done (split-phase: they signalled long ago)
+    if (!SM::kDouble) env.ex1_acquire();  // every reader of the previous transform's ex1 is done (split-phase)
 #pragma unroll
     for (int k0 = 0; k0 < 8; ++k0)
         ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
@@ -120,7 +137,7 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
     const int hi = tid >> 3, lo = tid & 7;
 #pragma unroll
     for (int b = 0; b < 8; ++b) x[b] = ex1[64 * hi + 8 * b + lo];
-    if (!SM::kAliased) env.ex1_release();
+    if (!SM::kAliased && !SM::kDouble) env.ex1_release();
     radix8<false>(x);
     env.tmem_wait_ld();
 #if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 2  /* what-if build: no inner exchange in the forward transform */
@@ -136,7 +153,7 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) x[c] = ex2[64 * hi + 8 * lo + (c ^ lo)];
 #endif
-    if (SM::kAliased) env.ex1_release();
+    if (SM::kAliased && !SM::kDouble) env.ex1_release();
     radix8<false>(x);
 }
 
@@ -144,14 +161,16 @@ template <class Env, class SM>
 PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
     const int tid = env.tid;
     const int hi = tid >> 3, lo = tid & 7;
-    double2* const ex1 = sm.e1();
-    double2* const ex2 = sm.e2();
+    const int par = SM::kDouble ? env.flip() : 0;
+    double2* const ex1 = sm.e1(par);
+    double2* const ex2 = sm.e2(par);
     uint32_t w[32];
     env.tmem_ld32(SM::kTw2, w);
     radix8<true>(x);
     env.tmem_wait_ld();
-    if (SM::kAliased) env.ex1_acquire();  // the previous transform's cross-team readers of this region are done
-    else env.warp_sync();                 // previous readers of ex2 are done
+    if (SM::kDouble) {}                        // a fresh buffer: nobody reads it any more (see TeamSmemTm2)
+    else if (SM::kAliased) env.ex1_acquire();  // the previous transform's cross-team readers of this region are done
+    else env.warp_sync();                      // previous readers of ex2 are done
     ex2[64 * hi + 8 * lo + lo] = x[0];
 #pragma unroll
     for (int c = 1; c < 8; ++c)
@@ -170,7 +189,7 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
 #pragma unroll
     for (int k0 = 0; k0 < 8; ++k0)
         x[k0] = cmul_conj(ex1[64 * k0 + tid], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
-    env.ex1_release();
+    if (!SM::kDouble) env.ex1_release();
     radix8<true>(x);
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul_conj(x[a], w32(a));

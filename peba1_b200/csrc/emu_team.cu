@@ -27,6 +27,8 @@ struct HostEnv {
     // tensor memory of the tensor-memory variant, emulated as a private array of 32-bit cells per thread
     int sums_col = 0;
     int tv_col = 480;
+    int xpar = 0;
+    int flip() { const int p = xpar; xpar ^= 1; return p; }
     uint32_t* tm = nullptr;
     void tmem_ld4(int col, uint32_t (&w)[4]) const { memcpy(w, tm + col, sizeof w); }
     void tmem_st4(int col, const uint32_t (&w)[4]) const { memcpy(tm + col, w, sizeof w); }
@@ -60,6 +62,7 @@ struct Shared {
     TeamSmem sm;
     TeamSmemTm sm_tm;
     TeamSmemTm1 sm_tm1;
+    TeamSmemTm2 sm_tm2;
     TeamSmemPair sm_pair;
     TwiddleTables tables;
     pthread_barrier_t team, warp[2];
@@ -101,6 +104,19 @@ void* worker(void* p) {
                 blind_rotate_team_tm<3, 7>(env, S->sm_tm, S->bkfft, S->n, pool, S->n + 1, job, u);
             else
                 blind_rotate_team_tm<2, 10>(env, S->sm_tm, S->bkfft, S->n, pool, S->n + 1, job, u);
+        }
+    } else if (S->mode == 6) {
+        std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
+        env.tm = tmem.data();
+        env.sums_col = 64 * (A->tid % 4);
+        tm_store_twiddles<TeamSmemTm2>(env, tw);
+        for (int64_t g = 0; g < S->count; ++g) {
+            PbsJob job{(int32_t)g, -1, 0, 1, 0};
+            int32_t* u = S->u_out + (size_t)g * (kN + 1);
+            if (S->L == 3 && S->Bgbit == 7)
+                blind_rotate_team_tm<3, 7>(env, S->sm_tm2, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
+            else
+                blind_rotate_team_tm<2, 10>(env, S->sm_tm2, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
         }
     } else if (S->mode == 5) {
         std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
@@ -242,6 +258,18 @@ int peba1_emu_bootstrap_woks_tm1(int L, int Bgbit, int n, const double* bkfft, c
     if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
     Shared* S = new Shared();
     S->mode = 5; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
+    S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+// double-buffered single exchange buffer, no mbarrier (TeamSmemTm2: the default kernel's layout)
+int peba1_emu_bootstrap_woks_tm2(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                                 int64_t count) {
+    if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
+    Shared* S = new Shared();
+    S->mode = 6; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
     S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
     int rc = run(S);
     delete S;

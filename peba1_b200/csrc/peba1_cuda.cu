@@ -127,6 +127,8 @@ struct DevEnvTm {
     uint32_t ex1_mbar = 0;    // smem address of the team's "exchange buffer free" mbarrier
     uint32_t ex1_phase = 1;   // parity to wait for: the buffer starts free (the phase before the first counts as done)
     int tv_col = 0;           // 16 tensor-memory columns where the decomposition input waits between digit levels
+    int xpar = 0;             // which exchange buffer the next transform uses (double-buffered layouts)
+    __device__ __forceinline__ int flip() { const int p = xpar; xpar ^= 1; return p; }
     // Split-phase write-after-read protection of the cross-team exchange buffer: a warp signals as soon as its reads
     // are done, the next writer waits just before writing, one whole transform pass later, so nobody actually blocks.
     __device__ __forceinline__ void ex1_release() const {
@@ -923,6 +925,19 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, kTeamsTm10 * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, counter);
         return 0;
     }
+    if (c->kernel_variant == 8 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
+        // as the default, on two alternating exchange buffers without the "buffer free" mbarrier (TeamSmemTm2).
+        // Measured 155.0 ms against 152.9 ms per 16,384: the buffer selection costs registers (84 B of spills).
+        const size_t smem = sizeof(TeamSmemTm2) * (size_t)kTeamsTm;
+        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+        const unsigned grid = std::min((unsigned)((count + kTeamsTm - 1) / kTeamsTm), (unsigned)c->sm_count);
+        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTm2>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
+        return 0;
+    }
     if (c->kernel_variant == 7 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // the default 8-team kernel with persistent CTAs
@@ -1111,7 +1126,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
-    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 7 ? atoi(v) : 1;  // tuning aid
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 8 ? atoi(v) : 1;  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
@@ -1603,7 +1618,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 7) return fail(PEBA1_EINVAL, "kernel_variant must be 0..7");
+        if (value < 0 || value > 8) return fail(PEBA1_EINVAL, "kernel_variant must be 0..8");
         c->kernel_variant = (int)value;
         return 0;
     }

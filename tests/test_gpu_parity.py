@@ -183,7 +183,7 @@ def test_kernel_variants_agree(engine, keys):
         assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), "tmk"
         engine.set_option("kernel_variant", 5)   # 10 teams per CTA on one exchange buffer; 45 jobs: 4.5 CTAs
         assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), "tm10"
-        for variant in (6, 7):                   # persistent CTAs drawing jobs from a counter (10 and 8 teams)
+        for variant in (6, 7, 8):                # persistent CTAs drawing jobs from a counter (10 / 8 teams, 2 buffers)
             engine.set_option("kernel_variant", variant)
             assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), variant
         engine.set_option("kernel_variant", 1)

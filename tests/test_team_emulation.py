@@ -75,3 +75,10 @@ def test_pair_variant_matches_exact_oracle(emu, oracle, keys):
                                             tin.ctypes.data_as(C.c_void_p), u5.ctypes.data_as(C.c_void_p),
                                             C.c_int64(3)) == 0
     assert np.array_equal(u5, u)
+    # two alternating exchange buffers, no "buffer free" barrier (TeamSmemTm2, the default kernel's layout): here the
+    # emulation is a real check of the hazard argument, the only synchronisation left is the transforms' own barriers
+    u6 = np.zeros((3, 1025), dtype=np.int32)
+    assert emu.peba1_emu_bootstrap_woks_tm2(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
+                                            tin.ctypes.data_as(C.c_void_p), u6.ctypes.data_as(C.c_void_p),
+                                            C.c_int64(3)) == 0
+    assert np.array_equal(u6, u)
