@@ -227,3 +227,32 @@ def test_device_side_encryption(engine, keys):
     # fresh encryptions are valid gate inputs
     out = engine.gate_batch_host("NAND", ct[:64], ct[64:128])
     assert np.array_equal(keys.decrypt(out), 1 - (bits[:64] & bits[64:128]))
+
+
+@pytest.mark.gpu
+def test_short_key_every_kernel_variant_against_the_oracle(oracle):
+    """n = 8 mask words (8 CMux steps): cheap enough to run EVERY blind-rotation variant and launch shape — fixed grids,
+    persistent CTAs, 8 and 10 teams, pairs, the TMA/tcgen05.cp key ring — on ragged batches, word for word against the
+    exact-integer oracle."""
+    import peba1_b200 as P
+    from peba1_b200.cuda import Params
+    po = oracle.default_params(128)
+    po.n = 8
+    K = oracle.Keys.generate(po, 5)
+    eng = P.Engine(Params(8, 1024, 1, 3, 7, 8, 2), device=0)
+    eng.load_keys(K.bk, K.ksk)
+    rng = np.random.default_rng(4)
+    try:
+        for n in (1, 37, 301):
+            a, b, c = (rng.integers(0, 2, size=n) for _ in range(3))
+            ca, cb, cc = K.encrypt(a, 1), K.encrypt(b, 2), K.encrypt(c, 3)
+            want = K.gate_batch("MUX", ca, cb, cc, mode=oracle.EXACT, threads=os.cpu_count() or 1)
+            assert np.array_equal(K.decrypt(want), np.where(a == 1, b, c))
+            for min_batch in (-1, 1):
+                eng.set_option("pair_min_batch", min_batch)
+                for variant in range(9):
+                    eng.set_option("kernel_variant", variant)
+                    assert np.array_equal(eng.gate_batch_host("MUX", ca, cb, cc), want), (n, min_batch, variant)
+    finally:
+        eng.close()
+        K.close()
