@@ -133,8 +133,8 @@ PEBA1_HD void radix8(double2 (&x)[8]) {
 
 // Forward transform.  In: x[a] = p[64a+tid] + i p[64a+tid+512] (thread tid of the team).
 // Out: x[k2] = F[k0 + 8 k1 + 64 k2] with k0 = tid>>3, k1 = tid&7.
-template <class Env>
-PEBA1_HD void team_fft_forward(Env& env, double2 (&x)[8], const TeamTwiddles& tw, TeamSmem& sm, int parity) {
+template <class Env, class SM>
+PEBA1_HD void team_fft_forward(Env& env, double2 (&x)[8], const TeamTwiddles& tw, SM& sm, int parity) {
     const int tid = env.tid;
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
@@ -158,8 +158,8 @@ PEBA1_HD void team_fft_forward(Env& env, double2 (&x)[8], const TeamTwiddles& tw
 
 // Inverse transform (unscaled).  In: x[k2] = G[k0 + 8 k1 + 64 k2], k0 = tid>>3, k1 = tid&7.
 // Out: x[a] = g[64a+tid] * zeta^-(64a+tid), i.e. real part -> coefficient 64a+tid, imaginary -> +512.
-template <class Env>
-PEBA1_HD void team_fft_inverse(Env& env, double2 (&x)[8], const TeamTwiddles& tw, TeamSmem& sm, int parity) {
+template <class Env, class SM>
+PEBA1_HD void team_fft_inverse(Env& env, double2 (&x)[8], const TeamTwiddles& tw, SM& sm, int parity) {
     const int tid = env.tid;
     const int hi = tid >> 3, lo = tid & 7;
     radix8<true>(x);

@@ -23,6 +23,7 @@
 #include "blind_rotate_tm.cuh"
 #include "blind_rotate_pair.cuh"
 #include "blind_rotate_tmk.cuh"
+#include "blind_rotate_wide.cuh"
 #include "twiddles_host.h"
 
 using namespace peba1;
@@ -606,6 +607,51 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// K0+K1, low-latency version (blind_rotate_wide.cuh): one CTA of 2l teams per bootstrap, for narrow circuit levels.
+struct DevEnvWide : DevEnv {
+    __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+    __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync 15, 128;" ::: "memory"); }
+    __device__ __forceinline__ void key_fetch(void* dst, const void* src, unsigned bytes, unsigned long long* mbar) const {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst), b = (uint32_t)__cvta_generic_to_shared(mbar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+    }
+    __device__ __forceinline__ void key_wait(unsigned long long* mbar, unsigned parity) const {
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(mbar);
+        uint32_t done;
+        do {
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(done) : "r"(b), "r"(parity) : "memory");
+        } while (!done);
+    }
+};
+template <int L, int BGBIT>
+__global__ void __launch_bounds__(2 * L * kTeam, 1)
+    pbs_kernel_wide(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
+                    const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WideSmem<2 * L>& sm = *reinterpret_cast<WideSmem<2 * L>*>(smem_raw);
+    const int team = threadIdx.x / kTeam;
+    DevEnvWide env;
+    env.tid = (int)(threadIdx.x % kTeam);
+    env.bar_id = team + 1;
+    TeamTwiddles tw;
+    load_twiddles_dev(env.tid, tw);
+    for (int64_t g = blockIdx.x; g < count; g += gridDim.x) {
+        if (env.tid == 0) {  // a fresh barrier per job: the parity of step i is i & 1
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sm.key_full[team])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        blind_rotate_wide<L, BGBIT>(env, sm, tw, team, bkfft, n, pool, pool_stride, jobs[g], u_out + g * (int64_t)kUStride);
+        __syncthreads();  // the shared accumulator is reused by the CTA's next job
+    }
+}
+
 // K3.  One team per key polynomial q = (i*rows + r)*2 + c.
 template <int TEAMS>
 __global__ void __launch_bounds__(TEAMS* kTeam, 1)
@@ -819,6 +865,7 @@ struct peba1_cuda_ctx {
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default),
                              // 2: shared-key, 3: two bootstraps per team (blind_rotate_pair.cuh) for wide batches
+    int64_t wide_max_batch = -1;  // >= 0: batches up to this size use the low-latency kernel; -1: the measured rule
     int tmk_stagger_ns = 0;       // variant 4: start-up delay per team index
     int64_t pair_min_batch = -1;  // variant 3 below this batch size falls back to variant 1; -1 = 8 per SM
     int64_t max_pbs_per_launch = 1 << 18;
@@ -977,6 +1024,20 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<(unsigned)c->sm_count, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u,
                                                                      c->d_job_counter);
+        return 0;
+    }
+    // Very narrow level: latency matters, not throughput — one CTA of 2l teams per bootstrap (2.5 ms per wave of 148
+    // against 4.6 ms for a lone team).  Measured cross-over with the throughput kernel's narrow shapes: up to one wave,
+    // and again for 2-3 waves (7.4 ms against 8.8 ms at 444); in between two lone teams per SM (4.8 ms) win.
+    const int64_t wave = c->sm_count;
+    const bool wide = c->wide_max_batch < 0 ? (count <= wave || (count > 2 * wave && count <= 3 * wave))
+                                            : count <= c->wide_max_batch;
+    if (c->kernel_variant == 1 && c->tm_teams == 0 && wide) {
+        const size_t smem = sizeof(WideSmem<2 * L>);
+        const unsigned grid = (unsigned)std::min<int64_t>(count, (int64_t)c->sm_count * 4);
+        auto k = pbs_kernel_wide<L, BGBIT>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, 2 * L * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
         return 0;
     }
     // Narrow levels (the long tail of a circuit: tens of gates per launch) cannot fill 148 SMs with 8 bootstraps per
@@ -1607,6 +1668,10 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         if (value == 0) value = 1;
         if (value != 1 && value != 2 && value != 4 && value != 6 && value != 8) return fail(PEBA1_EINVAL, "ks_group must be 1, 2, 4, 6 or 8");
         c->ks_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "wide_max_batch")) {
+        c->wide_max_batch = value;
         return 0;
     }
     if (!strcmp(name, "tmk_stagger_ns")) {
