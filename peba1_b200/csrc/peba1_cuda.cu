@@ -1026,12 +1026,10 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
                                                                      c->d_job_counter);
         return 0;
     }
-    // Very narrow level: latency matters, not throughput — one CTA of 2l teams per bootstrap (2.5 ms per wave of 148
-    // against 4.6 ms for a lone team).  Measured cross-over with the throughput kernel's narrow shapes: up to one wave,
-    // and again for 2-3 waves (7.4 ms against 8.8 ms at 444); in between two lone teams per SM (4.8 ms) win.
-    const int64_t wave = c->sm_count;
-    const bool wide = c->wide_max_batch < 0 ? (count <= wave || (count > 2 * wave && count <= 3 * wave))
-                                            : count <= c->wide_max_batch;
+    // Very narrow level (at most one bootstrap per SM): latency matters, not throughput — one CTA of 2l teams per
+    // bootstrap, 2.5 ms against 4.6 ms for a lone team.  Beyond one wave the throughput kernel's narrow shapes win
+    // (measured, scripts/prof_mid.py: 296 -> 4.8 ms with T=2 vs 4.9; 444 -> 5.9 ms with T=4 vs 7.4).
+    const bool wide = c->wide_max_batch < 0 ? count <= c->sm_count : count <= c->wide_max_batch;
     if (c->kernel_variant == 1 && c->tm_teams == 0 && wide) {
         const size_t smem = sizeof(WideSmem<2 * L>);
         const unsigned grid = (unsigned)std::min<int64_t>(count, (int64_t)c->sm_count * 4);
@@ -1043,8 +1041,10 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
     // Narrow levels (the long tail of a circuit: tens of gates per launch) cannot fill 148 SMs with 8 bootstraps per
     // CTA; fewer teams per CTA spread them over more SMs, where a team runs faster alone.
     int teams = c->tm_teams;
-    if (teams == 0) teams = count >= (int64_t)c->sm_count * 8 ? 8 : count >= (int64_t)c->sm_count * 4 ? 4
-                          : count >= (int64_t)c->sm_count * 2 ? 2 : 1;
+    // the smallest T that still fits the level into one CTA per SM: a bootstrap is the faster the fewer teams share its SM
+    // (one wave of T = 1 / 2 / 4 / 8 teams per SM: 4.6 / 4.8 / 5.9 / 10.9 ms)
+    if (teams == 0) teams = count <= (int64_t)c->sm_count ? 1 : count <= (int64_t)c->sm_count * 2 ? 2
+                          : count <= (int64_t)c->sm_count * 4 ? 4 : 8;
     switch (teams) {
         case 1: return launch_pbs_tm_t<L, BGBIT, 1>(c, pool, stride, jobs, count, u);
         case 2: return launch_pbs_tm_t<L, BGBIT, 2>(c, pool, stride, jobs, count, u);
