@@ -41,7 +41,10 @@ extern "C" {
 enum peba1_op {
     PEBA1_OP_NAND = 0, PEBA1_OP_AND = 1, PEBA1_OP_OR = 2, PEBA1_OP_XOR = 3, PEBA1_OP_XNOR = 4,
     PEBA1_OP_NOR = 5, PEBA1_OP_ANDNY = 6, PEBA1_OP_ANDYN = 7, PEBA1_OP_ORNY = 8, PEBA1_OP_ORYN = 9,
-    PEBA1_OP_MUX = 10
+    PEBA1_OP_MUX = 10,
+    /* 3-input gates, ONE bootstrap each (not in upstream TFHE's API; used by the optimised circuit modes only):
+       XOR3 = bootstrap(2(a+b+c) + 1/2), MAJ3 = bootstrap(a+b+c): sum and carry of a full adder */
+    PEBA1_OP_XOR3 = 11, PEBA1_OP_MAJ3 = 12
 };
 
 /* Input modifiers of one gate operand (the recorder folds bootsNOT / bootsCONSTANT into these). */

@@ -41,8 +41,11 @@ void peba1_set_eager(int eager);
    on trivial inputs (quirk Q6) and when its result is never used, so raw ciphertexts equal a per-gate evaluation.
    1 = FOLD: gates with constant, repeated or complementary operands become constants / aliases / cheaper gates at
    record time, and gates nobody consumes are dropped at flush.  2 = FOLD + the full adder's carry as one MUX
-   (2 bootstraps + 1 keyswitch) instead of 3 AND + 2 XOR.  Modes 1 and 2 keep every DECRYPTED result; raw ciphertexts
-   differ.  Changing the mode flushes first. */
+   (2 bootstraps + 1 keyswitch) instead of 3 AND + 2 XOR.  3 = FOLD + 3-input gates: a full adder is XOR3 + MAJ3, one
+   bootstrap each (PEBA1_OP_XOR3 / PEBA1_OP_MAJ3: 2(a+b+c)+1/2 and a+b+c, not in upstream's gate set), and the
+   squared distance is ONE carry-save column compression over all slots (squarer partial products + accumulator) with
+   a single final ripple add.  Modes 1-3 keep every DECRYPTED result, quirks included; raw ciphertexts differ.
+   Changing the mode flushes first. */
 void peba1_set_mode(int mode);
 int peba1_get_mode(void);
 

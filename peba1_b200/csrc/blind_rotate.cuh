@@ -14,12 +14,16 @@
 
 namespace peba1 {
 
-// One bootstrap job: t = (0, c0) + s0 * pool[in0] + s1 * pool[in1]   (in < 0: operand absent)
-struct __align__(16) PbsJob {
+// One bootstrap job: t = (0, c0) + s0 * pool[in0] + s1 * pool[in1] + s2 * pool[in2]   (in < 0: operand absent).
+// The third operand serves the 3-input gates (XOR3, MAJ3: a full adder in two bootstraps).
+struct __align__(8) PbsJob {
     int32_t in0, in1;
     int32_t c0;
     int16_t s0, s1;
+    int32_t in2 = -1;
+    int16_t s2 = 0, pad = 0;
 };
+static_assert(sizeof(PbsJob) == 24, "PbsJob layout");
 
 template <class Env>
 PEBA1_HD int32_t rot_diff(const int32_t* acc, int j, int abar) {
@@ -48,6 +52,7 @@ PEBA1_HD void blind_rotate_team(Env& env, TeamSmem& sm, const TeamTwiddles& tw, 
         uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
         if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
         if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
+        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
         sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
     }
     env.team_sync();

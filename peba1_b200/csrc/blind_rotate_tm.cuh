@@ -225,6 +225,7 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
         uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
         if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
         if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
+        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
         sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
     }
     env.team_sync();
@@ -374,6 +375,7 @@ PEBA1_HD void blind_rotate_team_tmsh(Env& env, TeamSmemTm& sm, const double2* __
         uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
         if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
         if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
+        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
         sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
     }
     env.team_sync();

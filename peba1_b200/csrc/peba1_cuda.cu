@@ -1377,8 +1377,8 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
     // validate everything before launching anything
     for (int64_t i = 0; i < count; ++i) {
         const peba1_gate& g = gates[i];
-        if (g.op < 0 || g.op > PEBA1_OP_MUX) return fail(PEBA1_EINVAL, "gate %lld: unknown op %d", (long long)i, g.op);
-        const int nin = g.op == PEBA1_OP_MUX ? 3 : 2;
+        if (g.op < 0 || g.op > PEBA1_OP_MAJ3) return fail(PEBA1_EINVAL, "gate %lld: unknown op %d", (long long)i, g.op);
+        const int nin = g.op >= PEBA1_OP_MUX ? 3 : 2;
         for (int q = 0; q < nin; ++q) {
             if (g.flags & PEBA1_IN_CONST(q)) {
                 if (g.in[q] != 0 && g.in[q] != 1) return fail(PEBA1_EINVAL, "gate %lld: constant operand must be 0 or 1", (long long)i);
@@ -1430,6 +1430,8 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
                 // u1 = PBS(-1/8 + a + b), u2 = PBS(-1/8 - a + c), out = KS((0,1/8) + u1 + u2)
                 PbsJob& j1 = pj[ip];
                 PbsJob& j2 = pj[ip + 1];
+                j1 = PbsJob{};
+                j2 = PbsJob{};
                 uint32_t c1 = 0u - kEighth, c2 = 0u - kEighth;
                 c1 += operand(g, 0, 1, &j1.in0, &j1.s0);
                 c1 += operand(g, 1, 1, &j1.in1, &j1.s1);
@@ -1441,10 +1443,25 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
                 k.u1 = (int32_t)ip + 1;
                 k.c0 = (int32_t)kEighth;
                 ip += 2;
+            } else if (g.op == PEBA1_OP_XOR3 || g.op == PEBA1_OP_MAJ3) {
+                // XOR3: 2(a+b+c) + 1/2 (phases -1/4, +1/4, -1/4, +1/4 for 0..3 ones); MAJ3: a+b+c (-3/8, -1/8, +1/8, +3/8)
+                const int s = g.op == PEBA1_OP_XOR3 ? 2 : 1;
+                PbsJob& j = pj[ip];
+                j = PbsJob{};
+                uint32_t cc = g.op == PEBA1_OP_XOR3 ? 4u * kEighth : 0u;
+                cc += operand(g, 0, s, &j.in0, &j.s0);
+                cc += operand(g, 1, s, &j.in1, &j.s1);
+                cc += operand(g, 2, s, &j.in2, &j.s2);
+                j.c0 = (int32_t)cc;
+                k.u0 = (int32_t)ip;
+                k.u1 = -1;
+                k.c0 = 0;
+                ip += 1;
             } else {
                 int c0, sa, sb;
                 gate_consts(g.op, &c0, &sa, &sb);
                 PbsJob& j = pj[ip];
+                j = PbsJob{};
                 uint32_t cc = (uint32_t)c0 * kEighth;
                 cc += operand(g, 0, sa, &j.in0, &j.s0);
                 cc += operand(g, 1, sb, &j.in1, &j.s1);
@@ -1468,7 +1485,7 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
 
 int peba1_cuda_gate_batch(peba1_cuda_ctx* c, int32_t op, const int64_t* in0, const int64_t* in1, const int64_t* in2, const int64_t* out, int64_t count) {
     if (count < 0 || (count > 0 && (!in0 || !in1 || !out))) return fail(PEBA1_EINVAL, "null slot array");
-    if (op == PEBA1_OP_MUX && count > 0 && !in2) return fail(PEBA1_EINVAL, "MUX needs three operands");
+    if (op >= PEBA1_OP_MUX && count > 0 && !in2) return fail(PEBA1_EINVAL, "MUX, XOR3 and MAJ3 need three operands");
     std::vector<peba1_gate> g((size_t)count);
     for (int64_t i = 0; i < count; ++i) {
         g[i].op = op;
@@ -1483,8 +1500,8 @@ int peba1_cuda_gate_batch(peba1_cuda_ctx* c, int32_t op, const int64_t* in0, con
 
 int peba1_cuda_gate_batch_host(peba1_cuda_ctx* c, int32_t op, const int32_t* ca, const int32_t* cb, const int32_t* cc, int32_t* out, int64_t count) {
     if (count < 0 || (count > 0 && (!ca || !cb || !out))) return fail(PEBA1_EINVAL, "null host buffer");
-    const bool mux = op == PEBA1_OP_MUX;
-    if (mux && count > 0 && !cc) return fail(PEBA1_EINVAL, "MUX needs three operands");
+    const bool mux = op >= PEBA1_OP_MUX;  // the three 3-input gates
+    if (mux && count > 0 && !cc) return fail(PEBA1_EINVAL, "MUX, XOR3 and MAJ3 need three operands");
     if (count == 0) return 0;
     const int nin = mux ? 3 : 2;
     if (int rc = peba1_cuda_pool_reserve(c, (nin + 1) * count)) return rc;

@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 OP = {"NAND": 0, "AND": 1, "OR": 2, "XOR": 3, "XNOR": 4, "NOR": 5,
-      "ANDNY": 6, "ANDYN": 7, "ORNY": 8, "ORYN": 9, "MUX": 10}
+      "ANDNY": 6, "ANDYN": 7, "ORNY": 8, "ORYN": 9, "MUX": 10, "XOR3": 11, "MAJ3": 12}
 
 IN_NEG = lambda i: 1 << i            # noqa: E731
 IN_CONST = lambda i: 1 << (4 + i)    # noqa: E731

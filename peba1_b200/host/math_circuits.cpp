@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <deque>
 #include <utility>
 
 #include "../../include/peba1_math.h"
@@ -64,6 +65,13 @@ struct Builder {
     Bit MUX(const Bit& s, const Bit& t, const Bit& f) const {
         return Bit::adopt(record_mux(e, s.handle(), t.handle(), f.handle()));
     }
+    // 3-input gates, one bootstrap each (mode 3 only)
+    Bit XOR3(const Bit& a, const Bit& b, const Bit& c) const {
+        return Bit::adopt(record_gate3(e, PEBA1_OP_XOR3, a.handle(), b.handle(), c.handle()));
+    }
+    Bit MAJ3(const Bit& a, const Bit& b, const Bit& c) const {
+        return Bit::adopt(record_gate3(e, PEBA1_OP_MAJ3, a.handle(), b.handle(), c.handle()));
+    }
     Word load(const LweSample* s, int bits) const {
         Word w;
         w.reserve((size_t)bits);
@@ -74,6 +82,10 @@ struct Builder {
     // reference bootsADD1bit (Math.cpp:27-50): sum = (a^b)^c ; c' = ((a&b) ^ (a&c)) ^ (c&b) — 4 XOR + 3 AND
     Bit full_adder(const Bit& a, const Bit& b, Bit& carry) const {
         const Bit c0 = carry;
+        if (recorder_mode() >= 3) {  // sum and carry in one bootstrap each
+            carry = MAJ3(a, b, c0);
+            return XOR3(a, b, c0);
+        }
         if (recorder_mode() >= 2) {  // optimised adder: carry' = (a == b) ? a : carry — one MUX on the shared a^b
             const Bit t = XOR(a, b);
             Bit sum2 = XOR(t, c0);
@@ -178,8 +190,49 @@ void check_vectors(const char* what, size_t na, size_t nb) {
     if (na != nb) perror("The two ciphertexts do not have the same size in a distance computation\n");
 }
 
+// Mode 3 body of the squared distance: every term of every slot's square (the diagonal bits d_i at weight 2^2i, the
+// cross products d_i d_j, i < j, at weight 2^(i+j+1)) and the incoming accumulator bits are thrown into 23 weight
+// columns, the columns are compressed with full adders (XOR3 + MAJ3: 3 bits of a column -> 1 bit + 1 carry) until at
+// most two bits are left in each, and ONE ripple add produces the sum.  Same value as the reference's
+// multiply-then-add chain: the distance is < 2^23 (128 * 255^2), so no carry leaves column 22 and bit 23 stays
+// untouched (Q5); d is still the reference's SUBNbit result, quirk Q1 included.  First-in first-out per column keeps
+// the compression tree shallow; the first levels are thousands of gates wide.
+void euclid_columns(const Builder& B, Word& acc, LweSample* const* a, LweSample* const* b, int slots, int bitsize) {
+    const int width = 23;
+    std::vector<std::deque<Bit>> col((size_t)width);
+    for (int j = 0; j < width; ++j)
+        if (acc[j].handle() != kFalse) col[j].push_back(acc[j]);
+    for (int s = 0; s < slots; ++s) {
+        const Word d = B.sub(B.load(b[s], bitsize), B.load(a[s], bitsize), bitsize);
+        for (int i = 0; i < bitsize; ++i) {
+            if (2 * i < width) col[2 * i].push_back(d[i]);
+            for (int j = i + 1; j < bitsize; ++j)
+                if (i + j + 1 < width) col[i + j + 1].push_back(B.AND(d[i], d[j]));
+        }
+    }
+    for (int j = 0; j < width; ++j) {
+        std::deque<Bit>& c = col[j];
+        while (c.size() > 2) {
+            const Bit x = c.front(); c.pop_front();
+            const Bit y = c.front(); c.pop_front();
+            const Bit z = c.front(); c.pop_front();
+            c.push_back(B.XOR3(x, y, z));
+            if (j + 1 < width) col[j + 1].push_back(B.MAJ3(x, y, z));
+        }
+    }
+    Word p, q;
+    for (int j = 0; j < width; ++j) {
+        p.push_back(col[j].size() > 0 ? col[j][0] : Bit::constant(false));
+        q.push_back(col[j].size() > 1 ? col[j][1] : Bit::constant(false));
+    }
+    Bit carry;
+    const Word sum = B.add(p, q, width, carry);
+    for (int j = 0; j < width; ++j) acc[j] = sum[j];
+}
+
 // shared body of HE_EuclideanDistance / Function_f: `acc` holds the 24 accumulator bits, 23 of which are summed
 void euclid_into(const Builder& B, Word& acc, LweSample* const* a, LweSample* const* b, int slots, int bitsize) {
+    if (recorder_mode() >= 3 && 2 * bitsize <= 23) return euclid_columns(B, acc, a, b, slots, bitsize);
     const int max_bits = 24;
     for (int i = 0; i < slots; ++i) {
         const Word d = B.sub(B.load(b[i], bitsize), B.load(a[i], bitsize), bitsize);

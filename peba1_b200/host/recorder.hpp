@@ -36,6 +36,7 @@ void release(Handle h);
 // recording
 Handle record_gate(Engine* e, int op, Handle a, Handle b);           // 2-input bootstrapped gate
 Handle record_mux(Engine* e, Handle sel, Handle if1, Handle if0);    // 2 bootstraps + 1 keyswitch
+Handle record_gate3(Engine* e, int op, Handle a, Handle b, Handle c);  // XOR3 / MAJ3: 1 bootstrap + 1 keyswitch
 Handle wire_from_host(Engine* e, const int32_t* words);              // queues an upload; returns a handle with 1 ref
 void flush(Engine* e);
 void fetch(Engine* e, Handle h, int32_t* words);                     // flushes if needed; applies the negation

@@ -341,6 +341,23 @@ Handle record_mux(Engine* e, Handle sel, Handle if1, Handle if0) {
     return push_node(e, g, 1 + std::max(l0, std::max(l1, l2)));
 }
 
+// 3-input gates in ONE bootstrap (PEBA1_OP_XOR3 / PEBA1_OP_MAJ3; not part of upstream's API, used by circuit mode 3):
+// sum and carry of a full adder.  Constant, repeated or complementary operands fold like any other gate.
+Handle record_gate3(Engine* e, int op, Handle a, Handle b, Handle c) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const Handle in[3] = {a, b, c};
+    Handle out;
+    const bool maj = op == PEBA1_OP_MAJ3;
+    if (try_fold(e, in, 3, [maj](const int* v) { return maj ? (v[0] + v[1] + v[2] >= 2) : (v[0] ^ v[1] ^ v[2]); }, &out))
+        return out;
+    peba1_gate g{};
+    g.op = op;
+    const int l0 = set_operand(g, 0, a), l1 = set_operand(g, 1, b), l2 = set_operand(g, 2, c);
+    g_stats.gates++;
+    g_stats.pbs += 1;
+    return push_node(e, g, 1 + std::max(l0, std::max(l1, l2)));
+}
+
 int recorder_mode() { return g_mode; }
 
 Handle wire_from_host(Engine* e, const int32_t* words) {
@@ -377,7 +394,7 @@ void flush(Engine* e) {
             for (size_t i = 0; i < nodes.size(); ++i) {
                 const peba1_gate nd = nodes[i];
                 if (g_wires[nd.out].refs == 1) {
-                    const int nin = nd.op == PEBA1_OP_MUX ? 3 : 2;
+                    const int nin = nd.op >= PEBA1_OP_MUX ? 3 : 2;
                     for (int q = 0; q < nin; ++q)
                         if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(nd.in[q]);
                     unref_wire(nd.out);
@@ -399,7 +416,7 @@ void flush(Engine* e) {
             g_stats.executed_pbs += nd.op == PEBA1_OP_MUX ? 2 : 1;
             peba1_gate& g = e->scratch[i];
             g = nd;
-            const int nin = nd.op == PEBA1_OP_MUX ? 3 : 2;
+            const int nin = nd.op >= PEBA1_OP_MUX ? 3 : 2;
             for (int q = 0; q < nin; ++q)
                 if (!(nd.flags & PEBA1_IN_CONST(q))) g.in[q] = g_wires[nd.in[q]].slot;
             g.out = g_wires[nd.out].slot = alloc_slot(e);
@@ -409,7 +426,7 @@ void flush(Engine* e) {
         g_stats.levels++;
         if (nodes.size() > g_stats.max_level_width) g_stats.max_level_width = nodes.size();
         for (const peba1_gate& nd : nodes) {
-            const int nin = nd.op == PEBA1_OP_MUX ? 3 : 2;
+            const int nin = nd.op >= PEBA1_OP_MUX ? 3 : 2;
             g_wires[nd.out].level = 0;
             for (int q = 0; q < nin; ++q)
                 if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(nd.in[q]);
@@ -814,7 +831,7 @@ void peba1_set_eager(int eager) { g_eager = eager != 0; }
 void peba1_set_mode(int mode) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     for (Engine* e : g_engines) flush(e);  // pending work was recorded under the old mode
-    g_mode = mode < 0 ? 0 : mode > 2 ? 2 : mode;
+    g_mode = mode < 0 ? 0 : mode > 3 ? 3 : mode;
 }
 int peba1_get_mode(void) { return g_mode; }
 void peba1_get_stats(peba1_host_stats* out) {

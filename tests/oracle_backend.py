@@ -60,7 +60,15 @@ class OracleBackend:
             idx = np.nonzero(arr["op"] == op)[0]
             a = np.stack([self._operand(arr[i], 0) for i in idx])
             b = np.stack([self._operand(arr[i], 1) for i in idx])
-            c = np.stack([self._operand(arr[i], 2) for i in idx]) if op == 10 else None
+            c = np.stack([self._operand(arr[i], 2) for i in idx]) if op >= 10 else None
+            if op in (11, 12):   # XOR3 = bootstrap(2(a+b+c) + 1/2), MAJ3 = bootstrap(a+b+c): prologue here, rest by the oracle
+                s = 2 if op == 11 else 1
+                t = (s * (a.astype(np.int64) + b + c)) & 0xFFFFFFFF
+                if op == 11:
+                    t[:, -1] = (t[:, -1] + (1 << 31)) & 0xFFFFFFFF
+                t = t.astype(np.uint32).view(np.int32)
+                outs[idx] = np.stack([self.K.keyswitch(self.K.bootstrap_woks(row)) for row in t])
+                continue
             outs[idx] = self.K.gate_batch(OPNAMES[int(op)], a, b, c, threads=threads)
         for i in range(count):
             self.pool[arr[i]["out"]] = outs[i]

@@ -69,6 +69,10 @@ class SimBackend:
                 s, t, f = (self._operand(g, q) for q in range(3))
                 out.append(t if s else f)
                 pbs += 2
+            elif op in (11, 12):
+                a, b, c = (self._operand(g, q) for q in range(3))
+                out.append(a ^ b ^ c if op == 11 else int(a + b + c >= 2))
+                pbs += 1
             else:
                 out.append(TRUTH[op](self._operand(g, 0), self._operand(g, 1)))
                 pbs += 1

@@ -274,7 +274,7 @@ def test_slots_are_recycled(env):
     assert ks.stats().live_slots < 64
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_fold_modes_keep_decrypted_results(env, mode):
     """constant folding + dead-gate elimination (mode 1) and MUX-carry adders (mode 2) change the
     number of bootstraps, never a decrypted result — including the reference's quirks (Q1, Q3)."""
@@ -325,7 +325,7 @@ def test_fold_mode_face_match_size(env):
     t = rng.integers(0, 255, size=128)
     probe = (t + 1) % 256
     counts = {}
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         L.peba1_set_mode(mode)
         ta, tp = _vec(ks, t, 7000)
         pa, pp = _vec(ks, probe, 8000)
@@ -343,6 +343,7 @@ def test_fold_mode_face_match_size(env):
     L.peba1_set_mode(0)
     print("PBS and levels per face match by mode:", counts)
     assert counts[0][0] == 215544 and counts[1][0] < 0.6 * counts[0][0] and counts[2][0] < counts[1][0]
+    assert counts[3][0] < 0.5 * counts[2][0] and counts[3][1] < counts[2][1]
 
 
 def test_encrypt_array_on_device_path(env):
@@ -409,3 +410,48 @@ def test_batched_authentication_service(env):
     sim.reset_schedule()
     G.authenticate_batch(ks, pv1, tv1, ks.encrypt(G.bits_of([bound], 24), 1), r0w[:1], r1w[:1], slots=slots, bits=8)
     assert len(sim.level_widths) == levels_batch
+
+
+def test_mode3_distance_equals_faithful_on_random_vectors(env):
+    """Circuit mode 3 (3-input adders, column-compressed squared distance) against the faithful circuit on the
+    simulator: random byte vectors with zero bytes sprinkled in (quirk Q1 fires in the subtraction), several slot
+    counts, an incoming non-zero accumulator; and every full-adder input combination."""
+    L, ks, sim = env
+    rng = np.random.default_rng(2027)
+
+    def run_mode(mode, x, y, acc0):
+        L.peba1_set_mode(mode)
+        xa, xp = _vec(ks, x, 100)
+        ya, yp = _vec(ks, y, 200)
+        res = ks.encrypt_int(int(acc0), 24, 300)
+        s0 = ks.stats()
+        L.peba1_math_euclidean(res, xp, yp, len(x), 8, ks.cloud)
+        pbs = ks.stats().executed_pbs - s0.executed_pbs
+        v = ks.decrypt_int(res, 24)
+        for arr in xa + ya:
+            ks.free_array(8, arr)
+        ks.free_array(24, res)
+        return v, pbs
+    try:
+        for slots in (1, 3, 8):
+            for trial in range(4):
+                x, y = rng.integers(0, 256, size=slots), rng.integers(0, 256, size=slots)
+                x[rng.integers(0, slots)] = 0
+                if trial % 2:
+                    y[rng.integers(0, slots)] = 0
+                acc0 = int(rng.integers(0, 1 << 12)) if trial >= 2 else 0
+                v0, p0 = run_mode(0, x, y, acc0)
+                v3, p3 = run_mode(3, x, y, acc0)
+                assert v3 == v0, (slots, trial, x, y, acc0)
+                assert p3 < 0.2 * p0
+        L.peba1_set_mode(3)
+        for x in range(8):                 # 3-bit adds: every full-adder input combination, carry-in included
+            for y in range(8):
+                ea, eb = ks.encrypt_int(x, 3, 400), ks.encrypt_int(y, 3, 401)
+                r, c = ks.new_array(3), ks.new_array(1)
+                L.peba1_math_add(r, ea, eb, c, 3, ks.cloud)
+                assert ks.decrypt_int(r, 3) == (x + y) % 8 and ks.decrypt_int(c, 1) == (x + y) >> 3
+                for arr, n in ((ea, 3), (eb, 3), (r, 3), (c, 1)):
+                    ks.free_array(n, arr)
+    finally:
+        L.peba1_set_mode(0)

@@ -34,6 +34,7 @@ def cpu_twin(gpu_keys, oracle):
     sk = L.peba1_new_keyset_from_arrays(p, gpu_keys.lwe_key.ctypes.data_as(i32p), gpu_keys.tlwe_key.ctypes.data_as(i32p),
                                         gpu_keys.bk.ctypes.data_as(i32p), gpu_keys.ksk.ctypes.data_as(i32p))
     twin = H.KeySet(p, sk)
+    twin._oracle_keys = K
     # force the engine creation while the oracle backend is installed, then restore the product default
     tmp = twin.new_array(2)
     L.bootsAND(twin.at(tmp, 0), twin.at(tmp, 0), twin.at(tmp, 1), twin.cloud)
@@ -145,7 +146,7 @@ def test_face_match_function_f_and_g(gpu_keys):
         gpu_keys.free_array(8, arr)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_fold_modes_on_gpu(gpu_keys, mode):
     """SURVEY.md §8f item 1 on real ciphertexts: fewer bootstraps, identical decrypted results (noise included)."""
     L = H.load_library()
@@ -252,3 +253,60 @@ def test_batched_authentication_with_device_generated_templates(gpu_keys):
     far = ((probes - tmpl) ** 2).sum(axis=1) > bound
     assert far.tolist() == [False, True, True]
     assert got == [int(r1[k]) if far[k] else int((-r0[k]) % 256) for k in range(K)]
+
+
+def test_three_input_gates_and_mode3_face_match(gpu_keys, cpu_twin):
+    """XOR3 / MAJ3 (one bootstrap each; the full adder of circuit mode 3) on real ciphertexts: truth tables on all 8
+    triples, phase margins, raw words equal to the oracle's bootstrap of the same linear combination; then a full-size
+    face match in mode 3 (about 21 k bootstraps instead of 215 k) with the decrypted verdicts of the faithful circuit."""
+    from oracle_backend import OracleBackend
+    import peba1_b200 as P
+    L = H.load_library()
+    ks = gpu_keys
+    eng = P.Engine.from_handle(ks.cuda_context(), P.default_params(128), device=0)
+    bits = np.array([[a, b, c] for a in (0, 1) for b in (0, 1) for c in (0, 1)] * 8)       # 64 triples
+    ca, cb, cc = (ks.encrypt(bits[:, q], 700 + q) for q in range(3))
+    for op, truth in (("XOR3", bits.sum(axis=1) & 1), ("MAJ3", (bits.sum(axis=1) >= 2).astype(int))):
+        got = eng.gate_batch_host(op, ca, cb, cc)
+        assert np.array_equal(ks.decrypt(got), truth), op
+        # raw parity: the oracle bootstraps the same prologue
+        s = 2 if op == "XOR3" else 1
+        t = (s * (ca.astype(np.int64) + cb + cc)) & 0xFFFFFFFF
+        if op == "XOR3":
+            t[:, -1] = (t[:, -1] + (1 << 31)) & 0xFFFFFFFF
+        t = t.astype(np.uint32).view(np.int32)
+        K = cpu_twin_oracle(cpu_twin)
+        want = np.stack([K.keyswitch(K.bootstrap_woks(row)) for row in t[:6]])
+        assert np.array_equal(got[:6], want), op
+        # inputs of the bootstrap sit at least 1/16 away from the decision boundary (nominal 1/8 resp. 1/4)
+        ph = K.phase(t).astype(np.float64) / 2.0**32
+        assert np.all(np.abs(ph) > 1 / 16) and np.all(np.abs(ph) < 0.5 - 1 / 16), op
+    # full-size face match, mode 3
+    rng = np.random.default_rng(3)
+    tmpl = rng.integers(0, 255, size=128)
+    probe = (tmpl + 1) % 256
+    def vec(values, seed):
+        arrs = [ks.encrypt_int(int(v), 8, seed + i) for i, v in enumerate(values)]
+        return arrs, (C.POINTER(H.LweSample) * len(arrs))(*arrs)
+    ta, tp = vec(tmpl, 5000)
+    pa, pp = vec(probe, 6000)
+    L.peba1_set_mode(3)
+    try:
+        for bound, expect in ((100, 1), (128, 0)):                        # distance is exactly 128
+            eb = ks.encrypt_int(bound, 24, 7000)
+            rb = ks.new_array(24)
+            s0 = ks.stats()
+            L.peba1_math_function_f(rb, pp, tp, 128, eb, 8, ks.cloud)
+            s1 = ks.stats()
+            assert s1.executed_pbs - s0.executed_pbs < 22000 and s1.levels - s0.levels < 120
+            assert ks.decrypt_int(rb, 24) == expect
+            ks.free_array(24, eb); ks.free_array(24, rb)
+    finally:
+        L.peba1_set_mode(0)
+    for arr in ta + pa:
+        ks.free_array(8, arr)
+
+
+def cpu_twin_oracle(twin):
+    """the oracle key object behind the cpu_twin fixture (same key material as the GPU keys)"""
+    return twin._oracle_keys
