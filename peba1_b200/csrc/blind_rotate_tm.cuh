@@ -243,14 +243,14 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
     for (int i = 0; i < n; ++i) {
         const int abar = sm.bara[i];
         if (abar == 0) continue;
-#ifndef PEBA1_TV_IN_TMEM
+#ifdef PEBA1_TV_IN_REGS
         uint32_t tv[16];
 #endif
 #pragma unroll 1
         for (int r = 0; r < ROWS; ++r) {
             const int poly = r >= L ? 1 : 0;
             const int p = r - poly * L;
-#ifdef PEBA1_TV_IN_TMEM
+#ifndef PEBA1_TV_IN_REGS  /* the default; -DPEBA1_TV_IN_REGS rebuilds the r1f kernel for comparison */
             // The rotated differences feed L digit levels.  Held in registers across the transforms they cost 16
             // registers and push the kernel into spilling (LDL/STL = 6 % of its L1 wavefronts); parked in tensor
             // memory between the levels they cost one store and L-1 loads per polynomial.
