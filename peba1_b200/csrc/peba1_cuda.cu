@@ -754,6 +754,75 @@ __global__ void __launch_bounds__(kKsThreads)
     }
 }
 
+// K2 for narrow levels: the keyswitch of ONE ciphertext split over S CTAs (coefficient ranges), partial sums added with
+// red.global.add (integer addition mod 2^32 commutes: same words as the one-CTA kernel).  A narrow circuit level is
+// latency-bound: one CTA walks 8,192 digit positions in 0.8 ms whatever the batch; split 16 ways that is ~0.1 ms.
+// ks_init_kernel first sets every output to (0, ..., 0, b' [+ b''] + c0).
+__global__ void ks_init_kernel(int n, int64_t stride, const int32_t* __restrict__ u, const KsJob* __restrict__ jobs,
+                               int64_t count, int32_t* __restrict__ pool) {
+    const int64_t g = blockIdx.x;
+    if (g >= count) return;
+    const KsJob job = jobs[g];
+    int32_t* out = pool + job.out_slot * stride;
+    for (int w = threadIdx.x; w < stride; w += blockDim.x) {
+        uint32_t v = 0;
+        if (w == n) {
+            v = (uint32_t)u[(int64_t)job.u0 * kUStride + kN] + (uint32_t)job.c0;
+            if (job.u1 >= 0) v += (uint32_t)u[(int64_t)job.u1 * kUStride + kN];
+        }
+        out[w] = (int32_t)v;
+    }
+}
+template <int T, int BASEBIT>
+__global__ void __launch_bounds__(kKsThreads)
+    keyswitch_split_kernel(const int32_t* __restrict__ ksk, int n, int64_t kstride, int64_t stride,
+                           const int32_t* __restrict__ u, const KsJob* __restrict__ jobs, int64_t count, int parts,
+                           int32_t* __restrict__ pool) {
+    constexpr int BASE = 1 << BASEBIT;
+    constexpr uint32_t PREC_OFFSET = 1u << (32 - (1 + BASEBIT * T));
+    __shared__ uint32_t abar[kN];
+    const int t = threadIdx.x;
+    const int64_t g = blockIdx.x / parts;
+    const int part = blockIdx.x % parts, span = kN / parts, i0 = part * span;
+    if (g >= count) return;
+    const KsJob job = jobs[g];
+    const int32_t* u0 = u + (int64_t)job.u0 * kUStride;
+    const int32_t* u1 = job.u1 >= 0 ? u + (int64_t)job.u1 * kUStride : nullptr;
+    for (int i = t; i < span; i += kKsThreads) {
+        uint32_t a = (uint32_t)u0[i0 + i];
+        if (u1) a += (uint32_t)u1[i0 + i];
+        abar[i] = a + PREC_OFFSET;
+    }
+    __syncthreads();
+    const int w0 = 4 * t;
+    if (w0 > n) return;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const uint32_t row_bytes = (uint32_t)kstride * 4u;
+    uint64_t p0 = reinterpret_cast<uint64_t>(ksk) + 16u * (uint32_t)t;
+    asm volatile("" : "+l"(p0));
+#pragma unroll 1
+    for (int i = 0; i < span; ++i) {
+        const uint32_t a = abar[i];
+        const uint32_t ki = (uint32_t)(i0 + i) * (T * (BASE - 1));
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            const uint32_t d = (a >> (32 - (j + 1) * BASEBIT)) & (BASE - 1);
+            if (d != 0) {
+                const uint32_t idx = d + ki + (uint32_t)(j * (BASE - 1) - 1);
+                uint64_t addr;
+                asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(row_bytes), "l"(p0));
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(addr));
+                acc.x -= v.x; acc.y -= v.y; acc.z -= v.z; acc.w -= v.w;
+            }
+        }
+    }
+    unsigned int* out = reinterpret_cast<unsigned int*>(pool + job.out_slot * stride);
+    const uint32_t r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (w0 + q <= n) atomicAdd(out + w0 + q, r[q]);
+}
+
 // K4.  out = sign*in + (0, cst); in < 0: absent.
 __global__ void linear_kernel(int32_t* __restrict__ pool, int64_t stride, int n, const int64_t* __restrict__ in,
                               const int32_t* __restrict__ sign, const int32_t* __restrict__ cst,
@@ -863,6 +932,7 @@ struct peba1_cuda_ctx {
     int teams_per_cta = 6;
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
+    int64_t ks_split = -1;   // CTAs per ciphertext in the keyswitch of a narrow level: -1 by batch size, 0 never, else fixed (power of 2)
     int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default),
                              // 2: shared-key, 3: two bootstraps per team (blind_rotate_pair.cuh) for wide batches
     int64_t wide_max_batch = -1;  // >= 0: batches up to this size use the low-latency kernel; -1: the measured rule
@@ -1092,6 +1162,23 @@ int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const Pbs
 int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t count, int32_t* pool) {
     if (count <= 0) return 0;
     const int G = c->ks_group;
+    // narrow level: one wave of CTAs, each ciphertext split over up to 16 of them
+    int parts = 1;
+    if (G == 1 && c->ks_split != 0) {
+        const int64_t room = (int64_t)c->sm_count * 12 / std::max<int64_t>(count, 1);
+        while (parts * 2 <= room && parts < 16) parts *= 2;
+        if (c->ks_split > 0) parts = (int)c->ks_split;
+    }
+    if (parts > 1) {
+        ks_init_kernel<<<(unsigned)count, 160, 0, c->stream>>>(c->p.n, c->pool_stride, u, jobs, count, pool);
+        keyswitch_split_kernel<8, 2><<<(unsigned)(count * parts), kKsThreads, 0, c->stream>>>(
+            c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, parts, pool);
+        CU(cudaGetLastError());
+        if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
+        c->stats.launches += 2;
+        c->stats.keyswitches += (uint64_t)count;
+        return 0;
+    }
     const unsigned grid = (unsigned)((count + G - 1) / G);
     switch (G) {
         case 2: keyswitch_kernel<8, 2, 2><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
@@ -1685,6 +1772,12 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         if (value == 0) value = 1;
         if (value != 1 && value != 2 && value != 4 && value != 6 && value != 8) return fail(PEBA1_EINVAL, "ks_group must be 1, 2, 4, 6 or 8");
         c->ks_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_split")) {
+        if (value > 1 && (value & (value - 1))) return fail(PEBA1_EINVAL, "ks_split must be a power of two");
+        if (value > 64) return fail(PEBA1_EINVAL, "ks_split must be at most 64");
+        c->ks_split = value;
         return 0;
     }
     if (!strcmp(name, "wide_max_batch")) {
