@@ -138,7 +138,17 @@ int peba1_cuda_get_stats(peba1_cuda_ctx* ctx, peba1_cuda_stats* out);
 int peba1_cuda_reset_stats(peba1_cuda_ctx* ctx);
 /* Measured FP64 FMA peak of this device (dependent-free DFMA loop on all SMs), in TFLOP/s. */
 int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* ctx, double* tflops);
-/* Kernel configuration knobs (variant selection for tuning; 0 = default). */
+/* Kernel configuration knobs: tuning aids and the measured alternatives kept for comparison.  Every
+   setting produces the same words.
+     kernel_variant   1 (default): tensor-memory accumulators; persistent 8-team CTAs for wide batches, narrow shapes
+                      and the low-latency kernel (one CTA per bootstrap) for narrow ones.  0: register accumulators.
+                      2: key rows shared by four teams through tensor memory.  3: two bootstraps per team.  4: key rows by
+                      TMA + tcgen05.cp into a tensor-memory ring.  5 / 6: 10 teams per CTA on one exchange buffer (fixed
+                      grid / persistent).  7: as 1 with the job counter forced on.  8: two alternating exchange buffers.
+     tm_teams         teams per CTA of the narrow shapes (0 = by batch size)      teams_per_cta   the same for variant 0
+     wide_max_batch   batches up to this size use the low-latency kernel (-1 = one bootstrap per SM at most)
+     ks_split         CTAs per ciphertext in the keyswitch of narrow levels (-1 = by batch size, 0 = never)
+     ks_group, pair_min_batch, tmk_stagger_ns, max_pbs_per_launch: see peba1_cuda.cu */
 int peba1_cuda_set_option(peba1_cuda_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

@@ -933,11 +933,11 @@ struct peba1_cuda_ctx {
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int64_t ks_split = -1;   // CTAs per ciphertext in the keyswitch of a narrow level: -1 by batch size, 0 never, else fixed (power of 2)
-    int kernel_variant = 1;  // 0: register accumulators (blind_rotate.cuh), 1: tensor-memory accumulators (default),
-                             // 2: shared-key, 3: two bootstraps per team (blind_rotate_pair.cuh) for wide batches
+    int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..8 are the
+                             // measured alternatives
     int64_t wide_max_batch = -1;  // >= 0: batches up to this size use the low-latency kernel; -1: the measured rule
     int tmk_stagger_ns = 0;       // variant 4: start-up delay per team index
-    int64_t pair_min_batch = -1;  // variant 3 below this batch size falls back to variant 1; -1 = 8 per SM
+    int64_t pair_min_batch = -1;  // variants 3..8 below this batch size fall back to variant 1's shapes; -1 = one full wave
     int64_t max_pbs_per_launch = 1 << 18;
     // stats
     bool timing = false;
