@@ -1111,14 +1111,17 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
     // Narrow levels (the long tail of a circuit: tens of gates per launch) cannot fill 148 SMs with 8 bootstraps per
     // CTA; fewer teams per CTA spread them over more SMs, where a team runs faster alone.
     int teams = c->tm_teams;
-    // the smallest T that still fits the level into one CTA per SM: a bootstrap is the faster the fewer teams share its SM
-    // (one wave of T = 1 / 2 / 4 / 8 teams per SM: 4.6 / 4.8 / 5.9 / 10.9 ms)
-    if (teams == 0) teams = count <= (int64_t)c->sm_count ? 1 : count <= (int64_t)c->sm_count * 2 ? 2
-                          : count <= (int64_t)c->sm_count * 4 ? 4 : 8;
+    // the smallest T (1..8) that still fits the level into one CTA per SM: a bootstrap is the faster the fewer teams share
+    // its SM (one wave of T = 1 / 2 / 4 / 8 teams per SM: 4.6 / 4.8 / 5.9 / 10.9 ms)
+    if (teams == 0) teams = (int)std::min<int64_t>(8, (count + c->sm_count - 1) / c->sm_count);
     switch (teams) {
         case 1: return launch_pbs_tm_t<L, BGBIT, 1>(c, pool, stride, jobs, count, u);
         case 2: return launch_pbs_tm_t<L, BGBIT, 2>(c, pool, stride, jobs, count, u);
+        case 3: return launch_pbs_tm_t<L, BGBIT, 3>(c, pool, stride, jobs, count, u);
         case 4: return launch_pbs_tm_t<L, BGBIT, 4>(c, pool, stride, jobs, count, u);
+        case 5: return launch_pbs_tm_t<L, BGBIT, 5>(c, pool, stride, jobs, count, u);
+        case 6: return launch_pbs_tm_t<L, BGBIT, 6>(c, pool, stride, jobs, count, u);
+        case 7: return launch_pbs_tm_t<L, BGBIT, 7>(c, pool, stride, jobs, count, u);
         default: return launch_pbs_tm_t<L, BGBIT, 8>(c, pool, stride, jobs, count, u);
     }
 }
@@ -1764,7 +1767,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "tm_teams")) {
-        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(PEBA1_EINVAL, "tm_teams must be 0, 1, 2, 4 or 8");
+        if (value < 0 || value > 8) return fail(PEBA1_EINVAL, "tm_teams must be 0..8");
         c->tm_teams = (int)value;
         return 0;
     }

@@ -25,7 +25,7 @@ for n in counts:
     eng.set_option("kernel_variant", 1); eng.set_option("wide_max_batch", 0)
     for t in (2, 4, 8):
         eng.set_option("tm_teams", t); out.append(f"T={t}: {run(g):6.2f}")
-    eng.set_option("tm_teams", 0)
+    eng.set_option("tm_teams", 0); out.append(f"auto: {run(g):6.2f}")
     eng.set_option("wide_max_batch", 1 << 30); out.append(f"wide: {run(g):6.2f}")
     eng.set_option("wide_max_batch", 0)
     eng.set_option("kernel_variant", 7); eng.set_option("pair_min_batch", 1); out.append(f"persistent8: {run(g):6.2f}")
