@@ -348,6 +348,135 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
     env.team_sync();
 }
 
+// Register-accumulator variant of blind_rotate_team_tm for 6 teams per SM (12 warps, up to 168 registers): the MAC
+// accumulators stay in registers for the whole step (no tcgen05.ld/st per row and none of the register moves ptxas wraps
+// around them), twiddles and the decomposition input stay in tensor memory.  Measured basis: 6 teams per SM deliver the
+// same throughput as 8 with the tensor-memory MAC (one wave: 8.3 ms for 888 vs 10.9 ms for 1,184).
+template <int L, int BGBIT, class Env, class SM>
+PEBA1_HD void blind_rotate_team_tmr(Env& env, SM& sm, const double2* __restrict__ bkfft, int n,
+                                   const int32_t* __restrict__ pool, int64_t pool_stride, PbsJob job,
+                                   int32_t* __restrict__ u_out) {
+    constexpr int ROWS = 2 * L;
+    constexpr uint32_t HALF_BG = 1u << (BGBIT - 1);
+    constexpr uint32_t MASK_BG = (1u << BGBIT) - 1;
+    uint32_t offset = 0;
+#pragma unroll
+    for (int p = 1; p <= L; ++p) offset += HALF_BG << (32 - p * BGBIT);
+    const int tid = env.tid;
+    const int sums = env.sums_col;  // kTmSums + 64 * (warp / 4)
+
+    // ---- prologue + mod-switch (identical to blind_rotate_team)
+    for (int w = tid; w <= n; w += kTeam) {
+        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
+        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
+        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
+        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
+        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
+    }
+    env.team_sync();
+    {
+        const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);
+        const int32_t mu = 1 << 29;
+        for (int j = tid; j < kN; j += kTeam) {
+            const int idx = (j - rot) & (2 * kN - 1);
+            sm.acc[0][j] = 0;
+            sm.acc[1][j] = (idx & kN) ? -mu : mu;
+        }
+    }
+    env.team_sync();
+
+    for (int i = 0; i < n; ++i) {
+        const int abar = sm.bara[i];
+        if (abar == 0) continue;
+        double2 sum0[8], sum1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sum0[q] = make_double2(0.0, 0.0); sum1[q] = make_double2(0.0, 0.0); }
+#ifdef PEBA1_TV_IN_REGS
+        uint32_t tv[16];
+#endif
+#pragma unroll 1
+        for (int r = 0; r < ROWS; ++r) {
+            const int poly = r >= L ? 1 : 0;
+            const int p = r - poly * L;
+#ifndef PEBA1_TV_IN_REGS  /* the default; -DPEBA1_TV_IN_REGS rebuilds the r1f kernel for comparison */
+            // The rotated differences feed L digit levels.  Held in registers across the transforms they cost 16
+            // registers and push the kernel into spilling (LDL/STL = 6 % of its L1 wavefronts); parked in tensor
+            // memory between the levels they cost one store and L-1 loads per polynomial.
+            uint32_t tv[16];
+            if (p == 0) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
+                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
+                }
+                env.tmem_st16(env.tv_col, tv);
+            } else {
+                env.tmem_wait_st();
+                env.tmem_ld16(env.tv_col, tv);
+                env.tmem_wait_ld();
+            }
+#else
+            if (p == 0) {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
+                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
+                }
+            }
+#endif
+            const int shift = 32 - (p + 1) * BGBIT;
+            double2 x[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                x[a] = make_double2(digit2d((tv[a] >> shift) & MASK_BG, HALF_BG), digit2d((tv[8 + a] >> shift) & MASK_BG, HALF_BG));
+            team_fft_forward_tm(env, x, sm);
+            // pointwise MAC against BK_i row r, accumulators in registers (6 teams per SM leave 168 registers per thread)
+            const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
+            // chunk q = (column q >> 1, bins 4 (q & 1) ..): the key values of chunk q+1 are requested before chunk q is
+            // multiplied (the same software pipeline as the tensor-memory MAC)
+            double2 b0[4], b1[4];
+#define PEBA1_RLDG(q, b)                                                                                   \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e)                                                          \
+        b[e] = env.ldg2(bk + (size_t)(2 * (4 * ((q) & 1) + e) + ((q) >> 1)) * 64);
+#define PEBA1_RMAC(q, b)                                                                                   \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
+        if ((q) >> 1) cfma(sum1[4 * ((q) & 1) + e], x[4 * ((q) & 1) + e], b[e]);                           \
+        else cfma(sum0[4 * ((q) & 1) + e], x[4 * ((q) & 1) + e], b[e]);                                    \
+    }
+            PEBA1_RLDG(0, b0)
+            PEBA1_RLDG(1, b1)
+            PEBA1_RMAC(0, b0)
+            PEBA1_RLDG(2, b0)
+            PEBA1_RMAC(1, b1)
+            PEBA1_RLDG(3, b1)
+            PEBA1_RMAC(2, b0)
+            PEBA1_RMAC(3, b1)
+#undef PEBA1_RLDG
+#undef PEBA1_RMAC
+        }
+        // inverse transforms and accumulator update (round to nearest, wrap mod 2^32)
+        team_fft_inverse_tm(env, sum0, sm);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            sm.acc[0][64 * a + tid] = (int32_t)((uint32_t)sm.acc[0][64 * a + tid] + d2u_rn(sum0[a].x));
+            sm.acc[0][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[0][64 * a + tid + 512] + d2u_rn(sum0[a].y));
+        }
+        team_fft_inverse_tm(env, sum1, sm);
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            sm.acc[1][64 * a + tid] = (int32_t)((uint32_t)sm.acc[1][64 * a + tid] + d2u_rn(sum1[a].x));
+            sm.acc[1][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[1][64 * a + tid + 512] + d2u_rn(sum1[a].y));
+        }
+        env.team_sync();
+    }
+
+    for (int j = tid; j < kN; j += kTeam)
+        u_out[j] = (j == 0) ? sm.acc[0][0] : (int32_t)(0u - (uint32_t)sm.acc[0][kN - j]);
+    if (tid == 0) u_out[kN] = sm.acc[1][0];
+    env.team_sync();
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // Shared-key variant.  In blind_rotate_team_tm every team streams the whole key row (16 KB) from L2 through the L1
 // data pipe for itself (ncu r1f: L1 hit rate 15 %, key loads = 23 points of the 78 % L1 pipe utilisation, 6.5 TB/s

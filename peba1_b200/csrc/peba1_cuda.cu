@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
 // K0+K1, tensor-memory version: 8 teams (512 threads, 16 warps) per CTA, one CTA per SM, <= 128 registers.
 constexpr int kTeamsTm = 8;
 constexpr int kTeamsTm10 = 10;  // with the single-exchange-buffer layout (TeamSmemTm1): 20 warps, 96 registers
-template <int L, int BGBIT, int TEAMS, class SM = TeamSmemTm>
+template <int L, int BGBIT, int TEAMS, class SM = TeamSmemTm, bool REGACC = false>
 __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     pbs_kernel_tm(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
                   const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out,
@@ -361,8 +361,12 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
             const int64_t g = next_job[team];
             env.team_sync();
             if (g >= count) break;
-            blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
-                                           u_out + g * (int64_t)kUStride);
+            if (REGACC)
+                blind_rotate_team_tmr<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
+                                                u_out + g * (int64_t)kUStride);
+            else
+                blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
+                                               u_out + g * (int64_t)kUStride);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1042,6 +1046,19 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, kTeamsTm10 * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, counter);
         return 0;
     }
+    if (c->kernel_variant == 9 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * 6)) {
+        // 6 teams per SM with the MAC accumulators in registers (blind_rotate_team_tmr), persistent CTAs
+        constexpr int T6 = 6;
+        const size_t smem = sizeof(TeamSmemTm) * (size_t)T6;
+        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+        const unsigned grid = std::min((unsigned)((count + T6 - 1) / T6), (unsigned)c->sm_count);
+        auto k = pbs_kernel_tm<L, BGBIT, T6, TeamSmemTm, true>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, T6 * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
+        return 0;
+    }
     if (c->kernel_variant == 8 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // as the default, on two alternating exchange buffers without the "buffer free" mbarrier (TeamSmemTm2).
@@ -1277,7 +1294,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
-    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 8 ? atoi(v) : 1;  // tuning aid
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 9 ? atoi(v) : 1;  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
@@ -1796,7 +1813,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 8) return fail(PEBA1_EINVAL, "kernel_variant must be 0..8");
+        if (value < 0 || value > 9) return fail(PEBA1_EINVAL, "kernel_variant must be 0..9");
         c->kernel_variant = (int)value;
         return 0;
     }

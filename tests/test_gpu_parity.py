@@ -250,7 +250,7 @@ def test_short_key_every_kernel_variant_against_the_oracle(oracle):
             assert np.array_equal(K.decrypt(want), np.where(a == 1, b, c))
             for min_batch in (-1, 1):
                 eng.set_option("pair_min_batch", min_batch)
-                for variant in range(9):
+                for variant in range(10):
                     eng.set_option("kernel_variant", variant)
                     assert np.array_equal(eng.gate_batch_host("MUX", ca, cb, cc), want), (n, min_batch, variant)
     finally:
