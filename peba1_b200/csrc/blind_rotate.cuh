@@ -34,6 +34,14 @@ PEBA1_HD int32_t rot_diff(const int32_t* acc, int j, int abar) {
     return (int32_t)((uint32_t)v - (uint32_t)acc[j]);
 }
 
+template <class Env>
+PEBA1_HD int32_t rot_only(const int32_t* acc, int j, int abar) {
+    // (X^abar * acc)[j] with negacyclic wrap; 0 < abar < 2N
+    const int idx = (j - abar) & (2 * kN - 1);
+    const int32_t v = acc[idx & (kN - 1)];
+    return (idx & kN) ? (int32_t)(0u - (uint32_t)v) : v;
+}
+
 // L = gadget length, BGBIT = log2 of the gadget base.  `u_out` receives the extracted sample (N+1 words).
 template <int L, int BGBIT, class Env>
 PEBA1_HD void blind_rotate_team(Env& env, TeamSmem& sm, const TeamTwiddles& tw, const double2* __restrict__ bkfft,

@@ -33,6 +33,9 @@ constexpr int kTmBk = 336;      // shared-key variant: 2 row buffers x 64 cells,
 struct __align__(16) TeamSmemTm {
     static constexpr bool kAliased = false, kDouble = false;
     static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;  // tensor-memory columns (8 teams: 4 x 64 sums)
+    // [320,384): decomposition input, 16 columns per warp group; [384,512): the thread's own accumulator words, 32 per
+    // warp group (see blind_rotate_team_tm).  The zero block of the other layouts is not needed: the sums are cleared.
+    static constexpr int kTv = 320, kOwn = 384;
     double2  ex1[kM];
     double2  ex2[kM];
     int32_t  acc[2][kN];
@@ -50,6 +53,7 @@ struct __align__(16) TeamSmemTm {
 struct __align__(16) TeamSmemTm1 {
     static constexpr bool kAliased = true, kDouble = false;
     static constexpr int kTw1 = 320, kTw2 = 352, kZero = 384;  // 10 teams: 5 x 64 columns of sums come first
+    static constexpr int kTv = 400, kOwn = -1;   // no columns left for the own-words copy
     double2  ex1[kM];
     int32_t  acc[2][kN];
     uint16_t bara[640];
@@ -66,6 +70,7 @@ struct __align__(16) TeamSmemTm1 {
 struct __align__(16) TeamSmemTm2 {
     static constexpr bool kAliased = true, kDouble = true;
     static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;
+    static constexpr int kTv = 320, kOwn = 384;
     double2  ex[2][kM];
     int32_t  acc[2][kN];
     uint16_t bara[640];
@@ -232,10 +237,25 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
     {
         const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);
         const int32_t mu = 1 << 29;
-        for (int j = tid; j < kN; j += kTeam) {
+        // Thread tid is the only one that ever UPDATES words tid + 64 k of the accumulator (k < 8: real slots, k >= 8:
+        // imaginary slots of its 8 transform points).  Its copy of those 16 words of the BODY polynomial also lives in
+        // tensor memory (SM::kOwn): the un-rotated operand of (X^abar - 1) ACC and the read half of the update then cost
+        // two tcgen05.ld per step instead of 32 shared-memory loads (-64 of ~3,075 L1 wavefronts per ciphertext-step).
+        uint32_t own[16], zero[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int j = tid + kTeam * k;
             const int idx = (j - rot) & (2 * kN - 1);
             sm.acc[0][j] = 0;
             sm.acc[1][j] = (idx & kN) ? -mu : mu;
+            own[k] = (uint32_t)((idx & kN) ? -mu : mu);
+            zero[k] = 0u;
+        }
+        if (SM::kOwn >= 0) {
+            env.tmem_st16(env.own_col, zero);
+            env.tmem_st16(env.own_col + 16, own);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) env.tmem_st16(sums + 16 * q, zero);  // the MAC accumulators start every step at 0
         }
     }
     env.team_sync();
@@ -256,10 +276,21 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
             // memory between the levels they cost one store and L-1 loads per polynomial.
             uint32_t tv[16];
             if (p == 0) {
+                if (SM::kOwn >= 0) {
+                    uint32_t own[16];
+                    env.tmem_ld16(env.own_col + 16 * poly, own);  // stored at the last update, several tcgen05.wait::st ago
+                    env.tmem_wait_ld();
 #pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
-                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
+                    for (int a = 0; a < 8; ++a) {
+                        tv[a] = (uint32_t)rot_only<Env>(sm.acc[poly], 64 * a + tid, abar) - own[a] + offset;
+                        tv[8 + a] = (uint32_t)rot_only<Env>(sm.acc[poly], 64 * a + tid + 512, abar) - own[8 + a] + offset;
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
+                        tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
+                    }
                 }
                 env.tmem_st16(env.tv_col, tv);
             } else {
@@ -286,10 +317,10 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
             // Software pipeline: the accumulators and key values of chunk q+1 are in flight while chunk q is
             // multiplied.  Row 0 reads its accumulators from the zero block (no branch, no register clearing).
             const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
-            if (r > 0) env.tmem_wait_st();  // the previous row's stores have landed
+            if (SM::kOwn >= 0 || r > 0) env.tmem_wait_st();  // the previous row's (or the clearing) stores have landed
             uint32_t w0[16], w1[16];
             double2 b0[4], b1[4];
-            const int zsel = r > 0 ? 1 : 0;
+            const int zsel = (SM::kOwn >= 0 || r > 0) ? 1 : 0;  // layouts with a zero block read row 0's accumulators there
 #define PEBA1_CHUNK_COL(q) (zsel ? sums + 32 * ((q) >> 1) + 16 * ((q) & 1) : SM::kZero)
 #if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 1  /* what-if build (scripts/ablate.sh): no key loads */
 #define PEBA1_CHUNK_LDG(q, b)                                                                              \
@@ -332,11 +363,32 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
         for (int c = 0; c < 2; ++c) {
             double2 s[8];
             tm_load8(env, sums + 32 * c, s);
-            team_fft_inverse_tm(env, s, sm);
+            if (SM::kOwn >= 0) {  // clear the column for the next step
+                uint32_t zero[16];
 #pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                sm.acc[c][64 * a + tid] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid] + d2u_rn(s[a].x));
-                sm.acc[c][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid + 512] + d2u_rn(s[a].y));
+                for (int k = 0; k < 16; ++k) zero[k] = 0u;
+                env.tmem_st16(sums + 32 * c, zero);
+                env.tmem_st16(sums + 32 * c + 16, zero);
+            }
+            team_fft_inverse_tm(env, s, sm);
+            if (SM::kOwn >= 0) {
+                uint32_t own[16];
+                env.tmem_ld16(env.own_col + 16 * c, own);
+                env.tmem_wait_ld();
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    own[a] += d2u_rn(s[a].x);
+                    own[8 + a] += d2u_rn(s[a].y);
+                    sm.acc[c][64 * a + tid] = (int32_t)own[a];
+                    sm.acc[c][64 * a + tid + 512] = (int32_t)own[8 + a];
+                }
+                env.tmem_st16(env.own_col + 16 * c, own);
+            } else {
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    sm.acc[c][64 * a + tid] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid] + d2u_rn(s[a].x));
+                    sm.acc[c][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid + 512] + d2u_rn(s[a].y));
+                }
             }
         }
         env.team_sync();

@@ -26,7 +26,8 @@ struct HostEnv {
     double2 ldg2(const double2* p) const { return *p; }
     // tensor memory of the tensor-memory variant, emulated as a private array of 32-bit cells per thread
     int sums_col = 0;
-    int tv_col = 480;
+    int tv_col = 340;
+    int own_col = 400;
     int xpar = 0;
     int flip() { const int p = xpar; xpar ^= 1; return p; }
     uint32_t* tm = nullptr;
@@ -122,6 +123,7 @@ void* worker(void* p) {
         std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
         env.tm = tmem.data();
         env.sums_col = 64 * (A->tid % 5);
+        env.tv_col = TeamSmemTm1::kTv + 16 * (A->tid % 5);  // this layout keeps its twiddles in [320, 384)
         tm_store_twiddles<TeamSmemTm1>(env, tw);
         for (int64_t g = 0; g < S->count; ++g) {
             PbsJob job{(int32_t)g, -1, 0, 1, 0};

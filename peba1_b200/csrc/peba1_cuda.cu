@@ -128,6 +128,7 @@ struct DevEnvTm {
     uint32_t ex1_mbar = 0;    // smem address of the team's "exchange buffer free" mbarrier
     uint32_t ex1_phase = 1;   // parity to wait for: the buffer starts free (the phase before the first counts as done)
     int tv_col = 0;           // 16 tensor-memory columns where the decomposition input waits between digit levels
+    int own_col = 0;          // 16 tensor-memory columns with this thread's own words of the body accumulator
     int xpar = 0;             // which exchange buffer the next transform uses (double-buffered layouts)
     __device__ __forceinline__ int flip() { const int p = xpar; xpar ^= 1; return p; }
     // Split-phase write-after-read protection of the cross-team exchange buffer: a warp signals as soon as its reads
@@ -333,7 +334,8 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 64 * (warp >> 2),
                  tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16)};
     env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
-    env.tv_col = SM::kZero + 16 + 16 * (warp >> 2);
+    env.tv_col = SM::kTv + 16 * (warp >> 2);
+    env.own_col = SM::kOwn + 32 * (warp >> 2);
     if ((warp >> 2) == 0) {  // one warp per lane quarter publishes the per-thread twiddles
         TeamTwiddles tw;
 #pragma unroll
