@@ -28,9 +28,9 @@ F_PBS = 630 * 258048            # FP64 flops per bootstrap: 162
 KSK_BYTES = 62029824            # non-zero keyswitch-key rows, unpadded
 KEY_SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this very
-# command at batch 16,384 (profiles/r1s_pbs_kernel_tm_ncu.txt, profiles/r1s_keyswitch_kernel_ncu.txt); reported as
+# command at batch 16,384 (profiles/r1zz_pbs_kernel_tm_final_ncu.txt, profiles/r1s_keyswitch_kernel_ncu.txt); reported as
 # roofline.traffic when the run uses that batch, null otherwise.
-NCU_TRAFFIC = {16384: {"blind_rotate": 622969856 + 77181696, "keyswitch": 402676992 + 43154688}}
+NCU_TRAFFIC = {16384: {"blind_rotate": 624066816 + 78354944, "keyswitch": 402676992 + 43154688}}
 
 
 def parse():
@@ -412,7 +412,7 @@ def main():
                      "note": "dominant kernel = blind rotation (FP64 vector pipe; neither hbm nor tensor applies). "
                              "achieved = 162,570,240 flop/PBS x PBS per launch / CUDA-event time of the launch; peak = "
                              "DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); traffic = "
-                             "DRAM bytes per launch from profiles/r1s_pbs_kernel_tm_ncu.txt (the key stays L2-resident)"},
+                             "DRAM bytes per launch from profiles/r1zz_pbs_kernel_tm_final_ncu.txt (the key stays L2-resident)"},
         "roofline_keyswitch": {"bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak,
                                "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"),
