@@ -19,12 +19,17 @@ def emu():
     return C.CDLL(os.path.join(CSRC, "libpeba1_emu.so"))
 
 
-def test_team_bootstrap_matches_exact_oracle(emu, oracle, keys):
+@pytest.fixture(scope="module")
+def bkfft(emu, keys):
+    """the bootstrapping key transformed by the emulated key_transform_team (all n rows are needed): once per module"""
     p = keys.params
-    # transform only the key rows is not possible (all n iterations are needed): full key transform, ~10 s
-    bkfft = np.zeros((p.n, 6, 8, 2, 64, 2), dtype=np.float64)
-    assert emu.peba1_emu_key_transform(keys.bk.ctypes.data_as(C.c_void_p), p.n, 6,
-                                       bkfft.ctypes.data_as(C.c_void_p)) == 0
+    out = np.zeros((p.n, 6, 8, 2, 64, 2), dtype=np.float64)
+    assert emu.peba1_emu_key_transform(keys.bk.ctypes.data_as(C.c_void_p), p.n, 6, out.ctypes.data_as(C.c_void_p)) == 0
+    return out
+
+
+def test_team_bootstrap_matches_exact_oracle(emu, oracle, keys, bkfft):
+    p = keys.params
     g = np.load(GOLDEN)
     tin = np.ascontiguousarray(g["pbs_in"][None, :])
     u = np.zeros((1, 1025), dtype=np.int32)
@@ -40,45 +45,39 @@ def test_team_bootstrap_matches_exact_oracle(emu, oracle, keys):
     assert np.array_equal(u2[0], g["pbs_out"])
 
 
-def test_pair_variant_matches_exact_oracle(emu, oracle, keys):
-    """Two bootstraps per team (blind_rotate_pair.cuh): an odd batch (the last team carries a shadow job), and one input
-    with zero mask words so that one ciphertext of a pair has a void step (abar == 0) while the other does not."""
-    from oracle import pyoracle
-    p = keys.params
-    bkfft = np.zeros((p.n, 6, 8, 2, 64, 2), dtype=np.float64)
-    assert emu.peba1_emu_key_transform(keys.bk.ctypes.data_as(C.c_void_p), p.n, 6,
-                                       bkfft.ctypes.data_as(C.c_void_p)) == 0
-    g = np.load(GOLDEN)
+def test_other_variants_match_exact_oracle_on_a_short_key(emu, oracle):
+    """The other team functions on a SHORT key (n = 48 CMux steps: the emulation's 64 CPU threads meet at some 30
+    barriers per step), against the exact-integer oracle with the same key:
+    two bootstraps per team (blind_rotate_pair.cuh) on an odd batch (the last team carries a shadow job) with one input
+    that has void steps (abar == 0) while its partner has none; the key-ring consumer (blind_rotate_tmk.cuh); the
+    single-exchange-buffer layouts (TeamSmemTm1, TeamSmemTm2)."""
+    po = oracle.default_params(128)
+    po.n = 48
+    K = oracle.Keys.generate(po, 11)
+    n = po.n
+    bkfft = np.zeros((n, 6, 8, 2, 64, 2), dtype=np.float64)
+    assert emu.peba1_emu_key_transform(K.bk.ctypes.data_as(C.c_void_p), n, 6, bkfft.ctypes.data_as(C.c_void_p)) == 0
     rng = np.random.default_rng(7)
-    tin = np.stack([g["pbs_in"], g["pbs_in"], g["pbs_in"]]).astype(np.int32)
-    tin[1, :8] = 0                                # void steps for ciphertext 1 only
+    tin = rng.integers(-2**31, 2**31, size=(3, n + 1), dtype=np.int64).astype(np.int32)
+    tin[1, :8] = 0                                 # void steps for ciphertext 1 only
     tin[1, 8:16] = rng.integers(-2**19, 2**19, 8)  # rounds to abar = 0 as well
-    tin[2] = np.roll(tin[2], 5)
     tin = np.ascontiguousarray(tin)
-    u = np.zeros((3, 1025), dtype=np.int32)
-    assert emu.peba1_emu_bootstrap_woks_pair(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
-                                             tin.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p),
-                                             C.c_int64(3)) == 0
-    assert np.array_equal(u[0], g["pbs_out"])
-    for k in (1, 2):
-        assert np.array_equal(u[k], keys.bootstrap_woks(tin[k], mode=pyoracle.EXACT)), k
-    # key rows through tensor memory (blind_rotate_tmk.cuh): chunk order and void steps (consumer side; the TMA /
-    # tcgen05.cp producer only exists on the device and is covered by the -m gpu variant test)
-    u4 = np.zeros((3, 1025), dtype=np.int32)
-    assert emu.peba1_emu_bootstrap_woks_tmk(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
-                                            tin.ctypes.data_as(C.c_void_p), u4.ctypes.data_as(C.c_void_p),
-                                            C.c_int64(3)) == 0
-    assert np.array_equal(u4, u)
-    # one exchange buffer for both exchanges (TeamSmemTm1, the 10-teams-per-SM layout)
-    u5 = np.zeros((3, 1025), dtype=np.int32)
-    assert emu.peba1_emu_bootstrap_woks_tm1(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
-                                            tin.ctypes.data_as(C.c_void_p), u5.ctypes.data_as(C.c_void_p),
-                                            C.c_int64(3)) == 0
-    assert np.array_equal(u5, u)
-    # two alternating exchange buffers, no "buffer free" barrier (TeamSmemTm2, the default kernel's layout): here the
-    # emulation is a real check of the hazard argument, the only synchronisation left is the transforms' own barriers
-    u6 = np.zeros((3, 1025), dtype=np.int32)
-    assert emu.peba1_emu_bootstrap_woks_tm2(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
-                                            tin.ctypes.data_as(C.c_void_p), u6.ctypes.data_as(C.c_void_p),
-                                            C.c_int64(3)) == 0
-    assert np.array_equal(u6, u)
+    want = np.stack([K.bootstrap_woks(t, mode=oracle.EXACT) for t in tin])
+
+    def run(fn, x):
+        x = np.ascontiguousarray(x)
+        u = np.zeros((x.shape[0], 1025), dtype=np.int32)
+        assert fn(3, 7, n, bkfft.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p),
+                  C.c_int64(x.shape[0])) == 0
+        return u
+    try:
+        assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_pair, tin), want)
+        # consumer side of the key ring (the TMA / tcgen05.cp producer only exists on the device: -m gpu variant tests)
+        assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tmk, tin[1:]), want[1:])
+        assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm1, tin[1:]), want[1:])
+        # two alternating exchange buffers, no "buffer free" barrier: here the emulation really checks the hazard
+        # argument, the only synchronisation left is the transforms' own barriers
+        assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm2, tin[1:]), want[1:])
+        assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm, tin), want)
+    finally:
+        K.close()
