@@ -35,9 +35,27 @@ got = ks.decrypt(allout)
 assert np.array_equal(got, expect), (rank, got, expect)
 lo, hi = G.shard_bounds(world * T, world, rank)
 assert hi - lo == T
+# BASELINE configs[4] plumbing (scripts/config5.py): no scatter at all — every rank derives ITS shard of the synthetic
+# gallery from the seed, encrypts it where it is used (peba1_encrypt_array_list_device; on the simulator the words are
+# made on the host), matches it in circuit mode 3, and only the encrypted match bits travel
+total = 7
+lo, hi = G.shard_bounds(total, world, rank)
+probe5, mine5, expect5 = G.synthetic_gallery_shard(total, lo, hi, slots, seed=9, planted=0.5, bound=bound)
+H.load_library().peba1_set_mode(3)
+tv = G.encrypt_templates_on_device(ks, mine5, bits, seed=1000 + lo)
+out5 = G.match_template_arrays(ks, ks.encrypt(G.bits_of(probe5, bits), 1), ks.encrypt(G.bits_of([bound], 24), 2), tv,
+                               slots, bits)
+H.load_library().peba1_set_mode(0)
+sizes = [G.shard_bounds(total, world, r)[1] - G.shard_bounds(total, world, r)[0] for r in range(world)]
+pad = np.zeros((max(sizes) - out5.shape[0], ks.words), dtype=np.int32)          # all_gather wants equal shapes
+all5 = G.gather_match_bits(dist, world, "cpu", torch, np.concatenate([out5, pad]))
+got5 = np.concatenate([ks.decrypt(all5[r * max(sizes): r * max(sizes) + sizes[r]]) for r in range(world)])
+whole = G.synthetic_gallery_shard(total, 0, total, slots, seed=9, planted=0.5, bound=bound)[2]
+assert np.array_equal(got5, whole), (rank, got5, whole)
 if rank == 0:
     assert 0 < expect.sum() < world * T        # both outcomes present
-    print("GLOO_OK", got.tolist())
+    assert 0 < whole.sum() < total
+    print("GLOO_OK", got.tolist(), got5.tolist())
 dist.destroy_process_group()
 '''
 
