@@ -1,11 +1,19 @@
 // peba1_cuda.cu — libpeba1_cuda: the sm_100a gate-bootstrapping engine behind include/peba1_cuda.h.
 //
 // Kernels:
-//   K0+K1  pbs_kernel          gate prologue, mod-switch, 630-step blind rotation, sample extraction
-//                              (replaces tfhe_bootstrap_woKS_FFT and everything below it)
-//   K2     keyswitch_kernel    lweKeySwitch over the extracted samples, writes the ciphertext pool
-//   K3     key_transform_kernel bootstrapping key -> transform domain, once per key
-//   K4     linear_kernel       bootsNOT / bootsCOPY / bootsCONSTANT on pool slots
+//   K0+K1  gate prologue, mod-switch, 630-step blind rotation, sample extraction (replaces tfhe_bootstrap_woKS_FFT and
+//          everything below it):
+//            pbs_kernel_tm       THE throughput kernel: one team of 64 threads per bootstrap, accumulators / twiddles /
+//                                decomposition input / own accumulator words in tensor memory, persistent CTAs
+//                                (blind_rotate_tm.cuh); also the narrow shapes with 1..8 teams per CTA
+//            pbs_kernel_wide     the latency kernel for at most one bootstrap per SM: one CTA of 2l teams per bootstrap,
+//                                rows in parallel, key rows by TMA (blind_rotate_wide.cuh)
+//            pbs_kernel, pbs_kernel_tmsh, pbs_kernel_pair, pbs_kernel_tmk: measured alternatives (kernel_variant 0, 2, 3, 4)
+//   K2     keyswitch_kernel (one CTA per ciphertext) / ks_init_kernel + keyswitch_split_kernel (narrow levels: a
+//          ciphertext split over up to 16 CTAs): lweKeySwitch over the extracted samples, writes the ciphertext pool
+//   K3     key_transform_kernel  bootstrapping key -> transform domain, once per key
+//   K4     linear_kernel         bootsNOT / bootsCOPY / bootsCONSTANT on pool slots
+//          lwe_encrypt_kernel    device-side encryption for synthetic inputs (peba1_cuda_encrypt_bits)
 // There is no CPU fallback in this file: every entry point needs a CUDA device.
 #include "../../include/peba1_cuda.h"
 
