@@ -44,7 +44,7 @@ void peba1_set_eager(int eager);
    (2 bootstraps + 1 keyswitch) instead of 3 AND + 2 XOR.  3 = FOLD + 3-input gates: a full adder is XOR3 + MAJ3, one
    bootstrap each (PEBA1_OP_XOR3 / PEBA1_OP_MAJ3: 2(a+b+c)+1/2 and a+b+c, not in upstream's gate set), and the
    squared distance is ONE carry-save column compression over all slots (squarer partial products + accumulator) with
-   a single final ripple add.  Modes 1-3 keep every DECRYPTED result, quirks included; raw ciphertexts differ.
+   a single final ripple add, fed by a borrow-chain |a - b| that reproduces the reference's subtraction defect.  Modes 1-3 keep every DECRYPTED result, quirks included; raw ciphertexts differ.
    Changing the mode flushes first. */
 void peba1_set_mode(int mode);
 int peba1_get_mode(void);

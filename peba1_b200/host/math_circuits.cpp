@@ -148,6 +148,30 @@ struct Builder {
         for (int i = 0; i <= bits; ++i) r.push_back(OR(neg_fixed[i], pos_part[i]));
         return r;
     }
+    // Mode 3 only: the low `bits` bits of bootsSUBNbit(a, b) — what the squared distance feeds to the multiplier
+    // (Math.cpp:352-356) — without the reference's two two's-complement passes.  d = a - b by a borrow chain
+    // (XOR3 / MAJ3), sign s = borrow out, result = (d ^ s) + s.  The reference's defect Q1 (for b = 0 it yields
+    // 2^bits - a, whose low bits are -a) is reproduced by forcing s when b is all zero.  Checked against the reference
+    // formula on every (a, 0), (0, b) and thousands of random pairs (tests/test_circuits.py).
+    Word absdiff_low(const Word& a, const Word& b, int bits) const {
+        Bit borrow = Bit::constant(false);
+        Word d;
+        for (int i = 0; i < bits; ++i) {
+            d.push_back(XOR3(a[i], b[i], borrow));
+            borrow = MAJ3(!a[i], b[i], borrow);
+        }
+        Bit any_b = b[0];
+        for (int i = 1; i < bits; ++i) any_b = OR(any_b, b[i]);
+        const Bit s = OR(borrow, !any_b);
+        Word r;
+        Bit carry = s;
+        for (int i = 0; i < bits; ++i) {
+            const Bit t = XOR(d[i], s);
+            r.push_back(XOR(t, carry));
+            if (i + 1 < bits) carry = AND(t, carry);
+        }
+        return r;
+    }
     // reference bootsMultiply (Math.cpp:214-250): shift-and-add over `width` bits (23 in the reference); each of the
     // `bits` partial products is accumulated with a (width-1)-bit ripple add, so bit width-1 stays trivially 0 (Q5)
     Word multiply(const Word& a, const Word& b, int bits, int width) const {
@@ -195,7 +219,7 @@ void check_vectors(const char* what, size_t na, size_t nb) {
 // columns, the columns are compressed with full adders (XOR3 + MAJ3: 3 bits of a column -> 1 bit + 1 carry) until at
 // most two bits are left in each, and ONE ripple add produces the sum.  Same value as the reference's
 // multiply-then-add chain: the distance is < 2^23 (128 * 255^2), so no carry leaves column 22 and bit 23 stays
-// untouched (Q5); d is still the reference's SUBNbit result, quirk Q1 included.  First-in first-out per column keeps
+// untouched (Q5); d = the low bits of the reference's SUBNbit result, quirk Q1 included (Builder::absdiff_low).  First-in first-out per column keeps
 // the compression tree shallow; the first levels are thousands of gates wide.
 void euclid_columns(const Builder& B, Word& acc, LweSample* const* a, LweSample* const* b, int slots, int bitsize) {
     const int width = 23;
@@ -203,7 +227,7 @@ void euclid_columns(const Builder& B, Word& acc, LweSample* const* a, LweSample*
     for (int j = 0; j < width; ++j)
         if (acc[j].handle() != kFalse) col[j].push_back(acc[j]);
     for (int s = 0; s < slots; ++s) {
-        const Word d = B.sub(B.load(b[s], bitsize), B.load(a[s], bitsize), bitsize);
+        const Word d = B.absdiff_low(B.load(b[s], bitsize), B.load(a[s], bitsize), bitsize);
         for (int i = 0; i < bitsize; ++i) {
             if (2 * i < width) col[2 * i].push_back(d[i]);
             for (int j = i + 1; j < bitsize; ++j)

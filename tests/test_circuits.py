@@ -455,3 +455,34 @@ def test_mode3_distance_equals_faithful_on_random_vectors(env):
                     ks.free_array(n, arr)
     finally:
         L.peba1_set_mode(0)
+
+
+def test_mode3_absdiff_matches_the_reference_subtraction_low_bits(env):
+    """Mode 3's squared distance uses its own |a - b| (borrow chain + conditional negate) instead of bootsSUBNbit.  One
+    slot of HE_EuclideanDistance is (low 8 bits of SUBNbit(probe, template))^2: checked against the reference formula
+    (|x - y| for y != 0, (-x) mod 256 for y = 0: quirk Q1) for every (x, 0), every (0, y) and random pairs."""
+    L, ks, sim = env
+    rng = np.random.default_rng(99)
+    pairs = [(x, 0) for x in range(256)] + [(0, y) for y in range(256)] + \
+            [tuple(int(v) for v in rng.integers(0, 256, 2)) for _ in range(600)] + [(255, 255), (255, 1), (1, 255), (128, 128)]
+    L.peba1_set_mode(3)
+    try:
+        for lo in range(0, len(pairs), 64):                      # 64 one-slot distances per batch
+            chunk = pairs[lo:lo + 64]
+            res, keep = [], []
+            L.peba1_batch_begin()
+            for x, y in chunk:
+                xa, xp = _vec(ks, [y], 100)                      # first vector = subtrahend (Math.cpp:352: SUB(b[i], a[i]))
+                ya, yp = _vec(ks, [x], 200)
+                r = ks.new_array(24)
+                L.peba1_math_euclidean(r, xp, yp, 1, 8, ks.cloud)
+                res.append(r); keep += xa + ya
+            L.peba1_batch_end()
+            for (x, y), r in zip(chunk, res):
+                d = abs(x - y) if y else (-x) % 256
+                assert ks.decrypt_int(r, 24) == d * d, (x, y)
+                ks.free_array(24, r)
+            for arr in keep:
+                ks.free_array(8, arr)
+    finally:
+        L.peba1_set_mode(0)
