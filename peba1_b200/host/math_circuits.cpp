@@ -219,8 +219,7 @@ void check_vectors(const char* what, size_t na, size_t nb) {
 // columns, the columns are compressed with full adders (XOR3 + MAJ3: 3 bits of a column -> 1 bit + 1 carry) until at
 // most two bits are left in each, and ONE ripple add produces the sum.  Same value as the reference's
 // multiply-then-add chain: the distance is < 2^23 (128 * 255^2), so no carry leaves column 22 and bit 23 stays
-// untouched (Q5); d = the low bits of the reference's SUBNbit result, quirk Q1 included (Builder::absdiff_low).  First-in first-out per column keeps
-// the compression tree shallow; the first levels are thousands of gates wide.
+// untouched (Q5); d = the low bits of the reference's SUBNbit result, quirk Q1 included (Builder::absdiff_low).
 void euclid_columns(const Builder& B, Word& acc, LweSample* const* a, LweSample* const* b, int slots, int bitsize) {
     const int width = 23;
     std::vector<std::deque<Bit>> col((size_t)width);
@@ -234,15 +233,25 @@ void euclid_columns(const Builder& B, Word& acc, LweSample* const* a, LweSample*
                 if (i + j + 1 < width) col[i + j + 1].push_back(B.AND(d[i], d[j]));
         }
     }
-    for (int j = 0; j < width; ++j) {
-        std::deque<Bit>& c = col[j];
-        while (c.size() > 2) {
-            const Bit x = c.front(); c.pop_front();
-            const Bit y = c.front(); c.pop_front();
-            const Bit z = c.front(); c.pop_front();
-            c.push_back(B.XOR3(x, y, z));
-            if (j + 1 < width) col[j + 1].push_back(B.MAJ3(x, y, z));
+    // Wallace passes: every pass compresses ALL columns by one layer of full adders (bits of the current layer only; the
+    // carries join the next layer of the column above), so the depth is ~log_1.5 of the tallest column (15 passes for
+    // 128 slots) instead of a chain that walks the columns one after the other (84 narrow levels).  Same adder count.
+    for (bool more = true; more;) {
+        std::vector<std::deque<Bit>> next((size_t)width);
+        for (int j = 0; j < width; ++j) {
+            std::deque<Bit>& c = col[j];
+            while (c.size() >= 3) {
+                const Bit x = c.front(); c.pop_front();
+                const Bit y = c.front(); c.pop_front();
+                const Bit z = c.front(); c.pop_front();
+                next[j].push_back(B.XOR3(x, y, z));
+                if (j + 1 < width) next[j + 1].push_back(B.MAJ3(x, y, z));
+            }
+            while (!c.empty()) { next[j].push_back(c.front()); c.pop_front(); }  // 0..2 leftovers move on unchanged
         }
+        col.swap(next);
+        more = false;
+        for (int j = 0; j < width; ++j) more |= col[j].size() > 2;
     }
     Word p, q;
     for (int j = 0; j < width; ++j) {

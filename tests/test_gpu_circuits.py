@@ -258,7 +258,7 @@ def test_batched_authentication_with_device_generated_templates(gpu_keys):
 def test_three_input_gates_and_mode3_face_match(gpu_keys, cpu_twin):
     """XOR3 / MAJ3 (one bootstrap each; the full adder of circuit mode 3) on real ciphertexts: truth tables on all 8
     triples, phase margins, raw words equal to the oracle's bootstrap of the same linear combination; then a full-size
-    face match in mode 3 (about 21 k bootstraps instead of 215 k) with the decrypted verdicts of the faithful circuit."""
+    face match in mode 3 (about 19 k bootstraps in 49 levels instead of 215 k in 377) with the decrypted verdicts of the faithful circuit."""
     from oracle_backend import OracleBackend
     import peba1_b200 as P
     L = H.load_library()
@@ -298,7 +298,7 @@ def test_three_input_gates_and_mode3_face_match(gpu_keys, cpu_twin):
             s0 = ks.stats()
             L.peba1_math_function_f(rb, pp, tp, 128, eb, 8, ks.cloud)
             s1 = ks.stats()
-            assert s1.executed_pbs - s0.executed_pbs < 22000 and s1.levels - s0.levels < 120
+            assert s1.executed_pbs - s0.executed_pbs < 19000 and s1.levels - s0.levels < 60
             assert ks.decrypt_int(rb, 24) == expect
             ks.free_array(24, eb); ks.free_array(24, rb)
     finally:
