@@ -486,3 +486,54 @@ def test_mode3_absdiff_matches_the_reference_subtraction_low_bits(env):
                 ks.free_array(8, arr)
     finally:
         L.peba1_set_mode(0)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_random_gate_dags_decrypt_the_same_in_every_mode(env, mode):
+    """Random circuits of boots* gates (constants, NOTs, copies, repeated and complementary operands, MUXes, dead gates)
+    recorded in a fold mode decrypt to the same bits as in the faithful mode — the recorder's constant folding,
+    aliasing and dead-gate elimination are semantics-preserving."""
+    L, ks, sim = env
+    two = {"AND": lambda a, b: a & b, "OR": lambda a, b: a | b, "XOR": lambda a, b: a ^ b, "XNOR": lambda a, b: 1 - (a ^ b),
+           "NAND": lambda a, b: 1 - (a & b), "NOR": lambda a, b: 1 - (a | b), "ANDNY": lambda a, b: (1 - a) & b,
+           "ANDYN": lambda a, b: a & (1 - b), "ORNY": lambda a, b: (1 - a) | b, "ORYN": lambda a, b: a | (1 - b)}
+    names = sorted(two)
+    rng = np.random.default_rng(500 + mode)
+    for trial in range(6):
+        nin, nnodes = 5, 40
+        inputs = rng.integers(0, 2, size=nin)
+        prog = []                                                  # (kind, operands...)
+        for k in range(nnodes):
+            kind = rng.choice(["g2", "g2", "g2", "mux", "not", "const", "copy"])
+            ops = [int(v) for v in rng.integers(0, nin + k, size=3)]
+            if rng.random() < 0.2:
+                ops[1] = ops[0]                                    # repeated operand
+            prog.append((kind, names[int(rng.integers(0, len(names)))], ops, int(rng.integers(0, 2))))
+        # plaintext evaluation
+        val = list(int(v) for v in inputs)
+        for kind, name, ops, cst in prog:
+            a, b, c = (val[o] for o in ops)
+            val.append({"g2": two[name](a, b), "mux": b if a else c, "not": 1 - a, "const": cst, "copy": a}[kind])
+        for m in (0, mode):
+            L.peba1_set_mode(m)
+            arr = ks.new_array(nin + nnodes)
+            ks.set_words(arr, ks.encrypt(inputs, 900 + trial))
+            at = lambda i: ks.at(arr, i)
+            L.peba1_batch_begin()
+            for k, (kind, name, ops, cst) in enumerate(prog):
+                out = at(nin + k)
+                if kind == "g2":
+                    getattr(L, "boots" + name)(out, at(ops[0]), at(ops[1]), ks.cloud)
+                elif kind == "mux":
+                    L.bootsMUX(out, at(ops[0]), at(ops[1]), at(ops[2]), ks.cloud)
+                elif kind == "not":
+                    L.bootsNOT(out, at(ops[0]), ks.cloud)
+                elif kind == "const":
+                    L.bootsCONSTANT(out, cst, ks.cloud)
+                else:
+                    L.bootsCOPY(out, at(ops[0]), ks.cloud)
+            L.peba1_batch_end()
+            got = ks.decrypt(ks.get_words(arr, nin + nnodes)).tolist()
+            assert got == val, (m, trial)
+            ks.free_array(nin + nnodes, arr)
+    L.peba1_set_mode(0)
