@@ -140,12 +140,13 @@ int peba1_cuda_reset_stats(peba1_cuda_ctx* ctx);
 int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* ctx, double* tflops);
 /* Kernel configuration knobs: tuning aids and the measured alternatives kept for comparison.  Every
    setting produces the same words.
-     kernel_variant   1 (default): tensor-memory accumulators; persistent 8-team CTAs for wide batches, narrow shapes
-                      and the low-latency kernel (one CTA per bootstrap) for narrow ones.  0: register accumulators.
-                      2: key rows shared by four teams through tensor memory.  3: two bootstraps per team.  4: key rows by
-                      TMA + tcgen05.cp into a tensor-memory ring.  5 / 6: 10 teams per CTA on one exchange buffer (fixed
-                      grid / persistent).  7: as 1 with the job counter forced on.  8: two alternating exchange buffers.  9: 6 teams per
-                      CTA with the accumulators in registers.
+     kernel_variant   1 (default): tensor-memory accumulators; persistent 8-team CTAs on two alternating exchange buffers
+                      for wide batches, narrow shapes and the low-latency kernel (one CTA per bootstrap) for narrow ones.
+                      0: register accumulators.  2: key rows shared by four teams through tensor memory.  3: two bootstraps
+                      per team.  4: key rows by TMA + tcgen05.cp into a tensor-memory ring.  5 / 6: 10 teams per CTA on one
+                      exchange buffer (fixed grid / persistent).  7: persistent 8-team CTAs on one cross-team exchange buffer
+                      guarded by an mbarrier (the default before).  8: the default's wide-batch kernel, also below one
+                      full wave.  9: 6 teams per CTA with the accumulators in registers.
      tm_teams         teams per CTA of the narrow shapes (0 = by batch size)      teams_per_cta   the same for variant 0
      wide_max_batch   batches up to this size use the low-latency kernel (-1 = one bootstrap per SM at most)
      ks_split         CTAs per ciphertext in the keyswitch of narrow levels (-1 = by batch size, 0 = never)

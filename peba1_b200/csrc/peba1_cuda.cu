@@ -4,8 +4,9 @@
 //   K0+K1  gate prologue, mod-switch, 630-step blind rotation, sample extraction (replaces tfhe_bootstrap_woKS_FFT and
 //          everything below it):
 //            pbs_kernel_tm       THE throughput kernel: one team of 64 threads per bootstrap, accumulators / twiddles /
-//                                decomposition input / own accumulator words in tensor memory, persistent CTAs
-//                                (blind_rotate_tm.cuh); also the narrow shapes with 1..8 teams per CTA
+//                                decomposition input / own accumulator words in tensor memory, persistent CTAs on two
+//                                alternating exchange buffers (TeamSmemTm2, blind_rotate_tm.cuh); also the narrow shapes
+//                                with 1..8 teams per CTA (TeamSmemTm)
 //            pbs_kernel_wide     the latency kernel for at most one bootstrap per SM: one CTA of 2l teams per bootstrap,
 //                                rows in parallel, key rows by TMA (blind_rotate_wide.cuh)
 //            pbs_kernel, pbs_kernel_tmsh, pbs_kernel_pair, pbs_kernel_tmk: measured alternatives (kernel_variant 0, 2, 3, 4)
@@ -947,7 +948,7 @@ struct peba1_cuda_ctx {
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int64_t ks_split = -1;   // CTAs per ciphertext in the keyswitch of a narrow level: -1 by batch size, 0 never, else fixed (power of 2)
-    int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..8 are the
+    int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..9 are the
                              // measured alternatives
     int64_t wide_max_batch = -1;  // >= 0: batches up to this size use the low-latency kernel; -1: the measured rule
     int tmk_stagger_ns = 0;       // variant 4: start-up delay per team index
@@ -1071,8 +1072,8 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
     }
     if (c->kernel_variant == 8 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
-        // as the default, on two alternating exchange buffers without the "buffer free" mbarrier (TeamSmemTm2).
-        // Measured 155.0 ms against 152.9 ms per 16,384: the buffer selection costs registers (84 B of spills).
+        // two alternating exchange buffers without the "buffer free" mbarrier (TeamSmemTm2): what the default does for
+        // wide batches; as a variant it also applies below one full wave (pair_min_batch)
         const size_t smem = sizeof(TeamSmemTm2) * (size_t)kTeamsTm;
         if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
@@ -1084,7 +1085,8 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
     }
     if (c->kernel_variant == 7 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
-        // the default 8-team kernel with persistent CTAs
+        // persistent 8-team CTAs on the single cross-team exchange buffer with its "buffer free" mbarrier (TeamSmemTm): the
+        // default until r1zz, 1.4 % slower than the two-buffer layout now
         const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
         if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
@@ -1113,11 +1115,14 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         return 0;
     }
     if (c->kernel_variant == 1 && c->tm_teams == 0 && count >= (int64_t)c->sm_count * kTeamsTm) {
-        // wide batch (the default path): one persistent 8-team CTA per SM, jobs drawn from a counter (= variant 7)
-        const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
+        // wide batch (the default path): one persistent 8-team CTA per SM, jobs drawn from a counter, on two alternating
+        // exchange buffers (= variant 8).  With the accumulator copies in tensor memory this instantiation has no spills
+        // left and needs no "buffer free" mbarrier: 149.3 ms per 16,384 against 151.35 ms for variant 7 (the default
+        // before; scripts/ubench/kbench.c, A-B-A on one box, identical output checksums).
+        const size_t smem = sizeof(TeamSmemTm2) * (size_t)kTeamsTm;
         if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
-        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTm>;
+        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTm2>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<(unsigned)c->sm_count, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u,
                                                                      c->d_job_counter);

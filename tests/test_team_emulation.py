@@ -43,6 +43,12 @@ def test_team_bootstrap_matches_exact_oracle(emu, oracle, keys, bkfft):
                                            tin.ctypes.data_as(C.c_void_p), u2.ctypes.data_as(C.c_void_p),
                                            C.c_int64(1)) == 0
     assert np.array_equal(u2[0], g["pbs_out"])
+    # the layout the default wide-batch kernel runs on: two alternating exchange buffers (TeamSmemTm2)
+    u3 = np.zeros((1, 1025), dtype=np.int32)
+    assert emu.peba1_emu_bootstrap_woks_tm2(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
+                                            tin.ctypes.data_as(C.c_void_p), u3.ctypes.data_as(C.c_void_p),
+                                            C.c_int64(1)) == 0
+    assert np.array_equal(u3[0], g["pbs_out"])
 
 
 def test_other_variants_match_exact_oracle_on_a_short_key(emu, oracle):
