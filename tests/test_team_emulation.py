@@ -87,3 +87,26 @@ def test_other_variants_match_exact_oracle_on_a_short_key(emu, oracle):
         assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm, tin), want)
     finally:
         K.close()
+
+
+def test_second_parameter_set_on_a_short_key(emu, oracle):
+    """l = 2, Bgbit = 10 (upstream's minimum_lambda <= 80 set: 4 key rows per CMux step, 10-bit digits) through the
+    register kernel code and both tensor-memory layouts, n = 40 CMux steps."""
+    po = oracle.default_params(80)
+    assert (po.l, po.Bgbit) == (2, 10)
+    po.n = 40
+    K = oracle.Keys.generate(po, 13)
+    n, rows = po.n, 2 * po.l
+    bkfft = np.zeros((n, rows, 8, 2, 64, 2), dtype=np.float64)
+    assert emu.peba1_emu_key_transform(K.bk.ctypes.data_as(C.c_void_p), n, rows, bkfft.ctypes.data_as(C.c_void_p)) == 0
+    rng = np.random.default_rng(17)
+    tin = np.ascontiguousarray(rng.integers(-2**31, 2**31, size=(2, n + 1), dtype=np.int64).astype(np.int32))
+    try:
+        want = np.stack([K.bootstrap_woks(t, mode=oracle.EXACT) for t in tin])
+        for fn in (emu.peba1_emu_bootstrap_woks, emu.peba1_emu_bootstrap_woks_tm, emu.peba1_emu_bootstrap_woks_tm2):
+            u = np.zeros((2, 1025), dtype=np.int32)
+            assert fn(2, 10, n, bkfft.ctypes.data_as(C.c_void_p), tin.ctypes.data_as(C.c_void_p),
+                      u.ctypes.data_as(C.c_void_p), C.c_int64(2)) == 0
+            assert np.array_equal(u, want)
+    finally:
+        K.close()
