@@ -1,16 +1,21 @@
-// emu_team.cu — CPU emulation of ONE team (64 threads) of the blind-rotation kernel.
+// emu_team.cu — CPU emulation of ONE team (64 threads) of the blind-rotation kernel (and of one 2l-team CTA of the
+// low-latency kernel).
 //
 // TEST INFRASTRUCTURE: this container has no GPU, so the `-m "not gpu"` tests run the very same
 // __host__ __device__ team code (negacyclic_fft.cuh, blind_rotate.cuh) with 64 CPU threads and pthread
 // barriers, and compare it with the oracle.  Never loaded by the product path.
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <vector>
 #include "blind_rotate.cuh"
 #include "blind_rotate_tm.cuh"
 #include "blind_rotate_pair.cuh"
 #include "blind_rotate_tmk.cuh"
+#include "blind_rotate_wide.cuh"
 #include "twiddles_host.h"
+
+#include <atomic>
 
 using namespace peba1;
 
@@ -193,9 +198,102 @@ int run(Shared* S) {
     return 0;
 }
 
+// ---- the low-latency kernel code (blind_rotate_wide.cuh): one CTA of 2l teams per bootstrap, 2l x 64 CPU threads
+template <int ROWS>
+struct WideShared {
+    WideSmem<ROWS> sm;
+    TwiddleTables tables;
+    pthread_barrier_t cta, pair, team[ROWS], warp[2 * ROWS];
+    std::atomic<int> fetched[ROWS];  // key rows that have "landed" per team: stands in for the TMA mbarrier
+    int n;
+    const double2* bkfft;
+    const int32_t* in_ct;
+    int32_t* u_out;
+    int64_t count;
+};
+template <int ROWS>
+struct WideEnv : HostEnv {
+    WideShared<ROWS>* S;
+    int my_team;
+    int waited = 0;  // key rows this thread has consumed
+    void cta_sync() { pthread_barrier_wait(&S->cta); }
+    void pair_sync() { pthread_barrier_wait(&S->pair); }
+    // the device issues an asynchronous bulk copy that completes on the mbarrier; here the copy is done on the spot and
+    // published by a release increment, and key_wait spins until as many rows have landed as this thread has asked for
+    void key_fetch(void* dst, const void* src, size_t bytes, unsigned long long*) {
+        memcpy(dst, src, bytes);
+        S->fetched[my_team].fetch_add(1, std::memory_order_release);
+    }
+    void key_wait(unsigned long long*, unsigned) {
+        ++waited;
+        while (S->fetched[my_team].load(std::memory_order_acquire) < waited) sched_yield();
+    }
+};
+template <int ROWS> struct WideArg { WideShared<ROWS>* S; int ctid; };
+
+template <int L, int BGBIT>
+void* wide_worker(void* p) {
+    constexpr int ROWS = 2 * L;
+    auto* A = (WideArg<ROWS>*)p;
+    WideShared<ROWS>* S = A->S;
+    const int team = A->ctid / kTeam, tid = A->ctid % kTeam;
+    WideEnv<ROWS> env;
+    env.tid = tid;
+    env.team = &S->team[team];
+    env.warp = &S->warp[2 * team + (tid >> 5)];
+    env.S = S;
+    env.my_team = team;
+    TeamTwiddles tw;
+    load_team_twiddles(S->tables, tid, tw);
+    for (int64_t g = 0; g < S->count; ++g) {
+        PbsJob job{(int32_t)g, -1, 0, 1, 0};
+        blind_rotate_wide<L, BGBIT>(env, S->sm, tw, team, S->bkfft, S->n, S->in_ct, S->n + 1, job,
+                                    S->u_out + (size_t)g * (kN + 1));
+        env.cta_sync();  // the kernel's job loop: nobody starts the next prologue before the outputs are written
+    }
+    return nullptr;
+}
+
+template <int L, int BGBIT>
+int run_wide(int n, const double2* bkfft, const int32_t* in_ct, int32_t* u_out, int64_t count) {
+    constexpr int ROWS = 2 * L;
+    auto* S = new WideShared<ROWS>();
+    S->n = n; S->bkfft = bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    build_twiddle_tables(S->tables);
+    pthread_barrier_init(&S->cta, nullptr, ROWS * kTeam);
+    pthread_barrier_init(&S->pair, nullptr, 2 * kTeam);
+    for (int r = 0; r < ROWS; ++r) {
+        pthread_barrier_init(&S->team[r], nullptr, kTeam);
+        pthread_barrier_init(&S->warp[2 * r], nullptr, 32);
+        pthread_barrier_init(&S->warp[2 * r + 1], nullptr, 32);
+        S->fetched[r].store(0);
+    }
+    std::vector<pthread_t> th(ROWS * kTeam);
+    std::vector<WideArg<ROWS>> args(ROWS * kTeam);
+    for (int t = 0; t < ROWS * kTeam; ++t) { args[t] = {S, t}; pthread_create(&th[t], nullptr, wide_worker<L, BGBIT>, &args[t]); }
+    for (int t = 0; t < ROWS * kTeam; ++t) pthread_join(th[t], nullptr);
+    pthread_barrier_destroy(&S->cta);
+    pthread_barrier_destroy(&S->pair);
+    for (int r = 0; r < ROWS; ++r) {
+        pthread_barrier_destroy(&S->team[r]);
+        pthread_barrier_destroy(&S->warp[2 * r]);
+        pthread_barrier_destroy(&S->warp[2 * r + 1]);
+    }
+    delete S;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
+// the low-latency kernel code (blind_rotate_wide.cuh): a CTA of 2l teams per bootstrap
+int peba1_emu_bootstrap_woks_wide(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                                  int64_t count) {
+    if (L == 3 && Bgbit == 7) return run_wide<3, 7>(n, (const double2*)bkfft, in_ct, u_out, count);
+    if (L == 2 && Bgbit == 10) return run_wide<2, 10>(n, (const double2*)bkfft, in_ct, u_out, count);
+    return -1;
+}
 
 // bk: int32 [n][rows][2][1024] -> bkfft: double2 [n][rows][8][2][64]
 int peba1_emu_key_transform(const int32_t* bk, int n, int rows, double* bkfft_out) {

@@ -49,6 +49,12 @@ def test_team_bootstrap_matches_exact_oracle(emu, oracle, keys, bkfft):
                                             tin.ctypes.data_as(C.c_void_p), u3.ctypes.data_as(C.c_void_p),
                                             C.c_int64(1)) == 0
     assert np.array_equal(u3[0], g["pbs_out"])
+    # the low-latency kernel code (blind_rotate_wide.cuh): 2l teams = 384 CPU threads on the one bootstrap
+    u4 = np.zeros((1, 1025), dtype=np.int32)
+    assert emu.peba1_emu_bootstrap_woks_wide(3, 7, p.n, bkfft.ctypes.data_as(C.c_void_p),
+                                             tin.ctypes.data_as(C.c_void_p), u4.ctypes.data_as(C.c_void_p),
+                                             C.c_int64(1)) == 0
+    assert np.array_equal(u4[0], g["pbs_out"])
 
 
 def test_other_variants_match_exact_oracle_on_a_short_key(emu, oracle):
@@ -85,6 +91,9 @@ def test_other_variants_match_exact_oracle_on_a_short_key(emu, oracle):
         # argument, the only synchronisation left is the transforms' own barriers
         assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm2, tin[1:]), want[1:])
         assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm, tin), want)
+        # the low-latency kernel does not skip void steps (all-zero digits instead): ciphertext 1 exercises that, and
+        # three jobs in a row the re-use of the key-row pipeline across jobs
+        assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_wide, tin), want)
     finally:
         K.close()
 
@@ -103,7 +112,8 @@ def test_second_parameter_set_on_a_short_key(emu, oracle):
     tin = np.ascontiguousarray(rng.integers(-2**31, 2**31, size=(2, n + 1), dtype=np.int64).astype(np.int32))
     try:
         want = np.stack([K.bootstrap_woks(t, mode=oracle.EXACT) for t in tin])
-        for fn in (emu.peba1_emu_bootstrap_woks, emu.peba1_emu_bootstrap_woks_tm, emu.peba1_emu_bootstrap_woks_tm2):
+        for fn in (emu.peba1_emu_bootstrap_woks, emu.peba1_emu_bootstrap_woks_tm, emu.peba1_emu_bootstrap_woks_tm2,
+                   emu.peba1_emu_bootstrap_woks_wide):
             u = np.zeros((2, 1025), dtype=np.int32)
             assert fn(2, 10, n, bkfft.ctypes.data_as(C.c_void_p), tin.ctypes.data_as(C.c_void_p),
                       u.ctypes.data_as(C.c_void_p), C.c_int64(2)) == 0
