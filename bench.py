@@ -128,8 +128,11 @@ def run_reference(args):
         "impl": "reference", "metric": "bootstrapped gates/s (PBS/s)", "value": rate, "unit": "PBS/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"gate-bootstrap microbench: boots{args.op} on random ciphertexts, n=630 N=1024 "
-                               f"(TFHE default 128-bit); CPU sample of {gates} gates per step",
+        # the own arm's workload (same string), of which every step here runs a bounded sample on the host cores
+        "config": {"workload": f"gate-bootstrap microbench (BASELINE configs[1]): batch of {args.batch} boots{args.op} per "
+                               "GPU on random ciphertexts, n=630 N=1024 k=1 l=3 Bgbit=7, keyswitch t=8 base 4",
+                   "batch_per_gpu": args.batch, "op": args.op,
+                   "sample": f"{gates} of the {args.batch} gates per step (a gate's cost does not depend on the batch)",
                    "batch_per_step": gates},
         "cpu_baseline": {"value": rate, "unit": "PBS/s", "cores": cores, "kind": "port",
                          "sample": f"{gates} boots{args.op} gates per step, one gate per thread, oracle FP64-FFT form "
