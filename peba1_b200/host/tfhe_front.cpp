@@ -78,7 +78,8 @@ static int g_batch_depth = 0;
 static bool g_eager = true;
 static peba1_host_stats g_stats{};
 static const peba1_test_backend* g_test_backend = nullptr;
-static int g_mode = 0;  // peba1_set_mode: 0 faithful, 1 fold + dead-gate elimination, 2 = 1 + MUX-carry adders
+static int g_mode = 0;  // peba1_set_mode: 0 faithful, 1 fold + dead-gate elimination, 2 = 1 + MUX-carry adders,
+                        // 3 = 1 + 3-input full adders (XOR3 / MAJ3) and carry-save column compression (math_circuits.cpp)
 
 // The four engine operations the recorder needs.  The product path is libpeba1_cuda; the table exists only so the
 // CPU test-suite can observe the schedule (tests/ installs a bit-level simulator).
