@@ -150,6 +150,7 @@ int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* ctx, double* tflops);
      tm_teams         teams per CTA of the narrow shapes (0 = by batch size)      teams_per_cta   the same for variant 0
      wide_max_batch   batches up to this size use the low-latency kernel (-1 = one bootstrap per SM at most)
      ks_split         CTAs per ciphertext in the keyswitch of narrow levels (-1 = by batch size, 0 = never)
+     narrow_two_buffers  1: the narrow shapes use the two-buffer layout of the wide-batch kernel too (default 0)
      ks_group, pair_min_batch, tmk_stagger_ns, max_pbs_per_launch: see peba1_cuda.cu */
 int peba1_cuda_set_option(peba1_cuda_ctx* ctx, const char* name, int64_t value);
 

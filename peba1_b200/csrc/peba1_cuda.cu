@@ -946,6 +946,7 @@ struct peba1_cuda_ctx {
     // options
     int teams_per_cta = 6;
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
+    int narrow_two_buffers = 0;  // 1: the narrow shapes (fixed grids of 1..8 teams) run on TeamSmemTm2 as well (not measured yet)
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int64_t ks_split = -1;   // CTAs per ciphertext in the keyswitch of a narrow level: -1 by batch size, 0 never, else fixed (power of 2)
     int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..9 are the
@@ -1018,15 +1019,21 @@ int launch_pbs_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const P
     return 0;
 }
 
-template <int L, int BGBIT, int TEAMS>
-int launch_pbs_tm_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
-                    int32_t* u) {
-    const size_t smem = sizeof(TeamSmemTm) * (size_t)TEAMS;
+template <int L, int BGBIT, int TEAMS, class SM>
+int launch_pbs_tm_ts(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
+                     int32_t* u) {
+    const size_t smem = sizeof(SM) * (size_t)TEAMS;
     const unsigned grid = (unsigned)((count + TEAMS - 1) / TEAMS);
-    auto k = pbs_kernel_tm<L, BGBIT, TEAMS>;
+    auto k = pbs_kernel_tm<L, BGBIT, TEAMS, SM>;
     CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, TEAMS * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, nullptr);
     return 0;
+}
+template <int L, int BGBIT, int TEAMS>
+int launch_pbs_tm_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
+                    int32_t* u) {
+    return c->narrow_two_buffers ? launch_pbs_tm_ts<L, BGBIT, TEAMS, TeamSmemTm2>(c, pool, stride, jobs, count, u)
+                                 : launch_pbs_tm_ts<L, BGBIT, TEAMS, TeamSmemTm>(c, pool, stride, jobs, count, u);
 }
 
 template <int L, int BGBIT>
@@ -1796,6 +1803,10 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         if (value == 0) value = 6;
         if (value < 1 || value > 6) return fail(PEBA1_EINVAL, "teams_per_cta must be 1..6");
         c->teams_per_cta = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "narrow_two_buffers")) {
+        c->narrow_two_buffers = value != 0;
         return 0;
     }
     if (!strcmp(name, "tm_teams")) {
