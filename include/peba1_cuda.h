@@ -146,7 +146,8 @@ int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* ctx, double* tflops);
                       per team.  4: key rows by TMA + tcgen05.cp into a tensor-memory ring.  5 / 6: 10 teams per CTA on one
                       exchange buffer (fixed grid / persistent).  7: persistent 8-team CTAs on one cross-team exchange buffer
                       guarded by an mbarrier (the default before).  8: the default's wide-batch kernel, also below one
-                      full wave.  9: 6 teams per CTA with the accumulators in registers.
+                      full wave.  9: 6 teams per CTA with the accumulators in registers.  10: as 8 with the inner exchange
+                      of the transforms by warp shuffles.
      tm_teams         teams per CTA of the narrow shapes (0 = by batch size)      teams_per_cta   the same for variant 0
      wide_max_batch   batches up to this size use the low-latency kernel (-1 = one bootstrap per SM at most)
      ks_split         CTAs per ciphertext in the keyswitch of narrow levels (-1 = by batch size, 0 = never)

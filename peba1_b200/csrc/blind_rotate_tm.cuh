@@ -31,7 +31,7 @@ constexpr int kTmBk = 336;      // shared-key variant: 2 row buffers x 64 cells,
 // Shared memory of one team in this version: ONE cross-team exchange buffer (two barriers per transform instead of
 // double buffering) so that 8 teams fit: 8 KB + 8 KB + 8 KB + 1.25 KB = 25.25 KB per team.
 struct __align__(16) TeamSmemTm {
-    static constexpr bool kAliased = false, kDouble = false;
+    static constexpr bool kAliased = false, kDouble = false, kShfl = false;
     static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;  // tensor-memory columns (8 teams: 4 x 64 sums)
     // [320,384): decomposition input, 16 columns per warp group; [384,512): the thread's own accumulator words, 32 per
     // warp group (see blind_rotate_team_tm).  The zero block of the other layouts is not needed: the sums are cleared.
@@ -51,7 +51,7 @@ struct __align__(16) TeamSmemTm {
 // [64 hi, 64 hi + 64) there, in both exchanges, and the eight threads of a region sit in one warp: the hazards between
 // the two uses are warp-local (__syncwarp), only the "buffer free" signal moves to after the LAST read of a transform.
 struct __align__(16) TeamSmemTm1 {
-    static constexpr bool kAliased = true, kDouble = false;
+    static constexpr bool kAliased = true, kDouble = false, kShfl = false;
     static constexpr int kTw1 = 320, kTw2 = 352, kZero = 384;  // 10 teams: 5 x 64 columns of sums come first
     static constexpr int kTv = 400, kOwn = -1;   // no columns left for the own-words copy
     double2  ex1[kM];
@@ -68,7 +68,7 @@ struct __align__(16) TeamSmemTm1 {
 // transforms after it was read, and the team barrier of the transform in between separates the two: a thread passes that
 // barrier only when every thread of the team has arrived at it, i.e. has finished the reads of the transform before.
 struct __align__(16) TeamSmemTm2 {
-    static constexpr bool kAliased = true, kDouble = true;
+    static constexpr bool kAliased = true, kDouble = true, kShfl = false;
     static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;
     static constexpr int kTv = 320, kOwn = 384;
     double2  ex[2][kM];
@@ -79,6 +79,33 @@ struct __align__(16) TeamSmemTm2 {
     PEBA1_HD double2* e1(int par) { return ex[par]; }
     PEBA1_HD double2* e2(int par) { return ex[par]; }
 };
+
+// TeamSmemTm2 with the INNER exchange of a transform (the 8 x 8 transposition between the lane index inside an 8-lane
+// group and the register index) done by warp shuffles instead of shared memory: three butterfly stages, each swapping one
+// bit between the two indices with __shfl_xor (north_star: "warp-shuffle butterflies").  A complex double is four 32-bit
+// shuffles, and every stage moves half of a thread's 8 values: 48 SHFL + the selects that pick what to send and where to
+// put what arrives (a lane-dependent choice between two registers, per value), against 8 STS.128 + 8 LDS.128.  Same
+// arithmetic, same words.  kernel_variant 10; not measured yet (written after the round's GPU budget was spent).
+struct __align__(16) TeamSmemTm2S : TeamSmemTm2 {
+    static constexpr bool kShfl = true;
+};
+
+// In-place transposition x[j] of lane l  <->  x[l] of lane j over the 8 lanes that share tid >> 3 (lo = tid & 7).
+template <class Env>
+PEBA1_HD void lane8_transpose(Env& env, double2 (&x)[8], int lo) {
+#pragma unroll
+    for (int m = 4; m >= 1; m >>= 1) {
+        const bool up = (lo & m) != 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j & m) continue;
+            // lanes with bit m clear keep x[j] and trade x[j | m]; their partners (bit m set) keep x[j | m] and trade x[j]
+            const double2 out = up ? x[j] : x[j | m];
+            const double2 in = env.shfl_xor_c(out, m);
+            if (up) x[j] = in; else x[j | m] = in;
+        }
+    }
+}
 
 PEBA1_HD double2 words_to_c(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
 #ifdef __CUDA_ARCH__
@@ -149,14 +176,20 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
 #else
-    if (SM::kAliased) env.warp_sync();  // the region's eight readers above are done before it is rewritten
-    ex2[64 * hi + lo] = x[0];
+    if (SM::kShfl) {
 #pragma unroll
-    for (int k1 = 1; k1 < 8; ++k1)
-        ex2[64 * hi + 8 * k1 + (lo ^ k1)] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
-    env.warp_sync();
+        for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
+        lane8_transpose(env, x, lo);
+    } else {
+        if (SM::kAliased) env.warp_sync();  // the region's eight readers above are done before it is rewritten
+        ex2[64 * hi + lo] = x[0];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) x[c] = ex2[64 * hi + 8 * lo + (c ^ lo)];
+        for (int k1 = 1; k1 < 8; ++k1)
+            ex2[64 * hi + 8 * k1 + (lo ^ k1)] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
+        env.warp_sync();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = ex2[64 * hi + 8 * lo + (c ^ lo)];
+    }
 #endif
     if (SM::kAliased && !SM::kDouble) env.ex1_release();
     radix8<false>(x);
@@ -173,19 +206,27 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
     env.tmem_ld32(SM::kTw2, w);
     radix8<true>(x);
     env.tmem_wait_ld();
-    if (SM::kDouble) {}                        // a fresh buffer: nobody reads it any more (see TeamSmemTm2)
-    else if (SM::kAliased) env.ex1_acquire();  // the previous transform's cross-team readers of this region are done
-    else env.warp_sync();                      // previous readers of ex2 are done
-    ex2[64 * hi + 8 * lo + lo] = x[0];
+    if (SM::kShfl) {
 #pragma unroll
-    for (int c = 1; c < 8; ++c)
-        ex2[64 * hi + 8 * lo + (c ^ lo)] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
-    env.tmem_ld32(SM::kTw1, w);
-    env.warp_sync();
+        for (int c = 1; c < 8; ++c) x[c] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+        env.tmem_ld32(SM::kTw1, w);
+        lane8_transpose(env, x, lo);
+    } else {
+        if (SM::kDouble) {}                        // a fresh buffer: nobody reads it any more (see TeamSmemTm2)
+        else if (SM::kAliased) env.ex1_acquire();  // the previous transform's cross-team readers of this region are done
+        else env.warp_sync();                      // previous readers of ex2 are done
+        ex2[64 * hi + 8 * lo + lo] = x[0];
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) x[k1] = ex2[64 * hi + 8 * k1 + (lo ^ k1)];
+        for (int c = 1; c < 8; ++c)
+            ex2[64 * hi + 8 * lo + (c ^ lo)] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
+        env.tmem_ld32(SM::kTw1, w);
+        env.warp_sync();
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) x[k1] = ex2[64 * hi + 8 * k1 + (lo ^ k1)];
+    }
     radix8<true>(x);
-    if (SM::kAliased) env.warp_sync();    // the region's readers above are done before it is rewritten
+    if (SM::kShfl) {}                     // kDouble layout, inner exchange not in memory: a fresh buffer
+    else if (SM::kAliased) env.warp_sync();    // the region's readers above are done before it is rewritten
     else env.ex1_acquire();               // previous readers of ex1 are done
 #pragma unroll
     for (int b = 0; b < 8; ++b) ex1[64 * hi + 8 * b + lo] = x[b];

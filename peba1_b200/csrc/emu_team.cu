@@ -27,6 +27,16 @@ struct HostEnv {
     pthread_barrier_t* warp;
     void team_sync() { pthread_barrier_wait(team); }
     void warp_sync() { pthread_barrier_wait(warp); }
+    // __shfl_xor of a complex double: publish, meet, read the partner's value, meet again before the slot is reused
+    double2* shfl_slots = nullptr;  // one per lane of this warp
+    double2 shfl_xor_c(double2 v, int mask) {
+        const int lane = tid & 31;
+        shfl_slots[lane] = v;
+        pthread_barrier_wait(warp);
+        const double2 r = shfl_slots[lane ^ mask];
+        pthread_barrier_wait(warp);
+        return r;
+    }
     int32_t ldg(const int32_t* p) const { return *p; }
     double2 ldg2(const double2* p) const { return *p; }
     // tensor memory of the tensor-memory variant, emulated as a private array of 32-bit cells per thread
@@ -69,6 +79,8 @@ struct Shared {
     TeamSmemTm sm_tm;
     TeamSmemTm1 sm_tm1;
     TeamSmemTm2 sm_tm2;
+    TeamSmemTm2S sm_tm2s;
+    double2 shfl_slots[2][32];
     TeamSmemPair sm_pair;
     TwiddleTables tables;
     pthread_barrier_t team, warp[2];
@@ -88,6 +100,7 @@ void* worker(void* p) {
     ThreadArg* A = (ThreadArg*)p;
     Shared* S = A->S;
     HostEnv env{A->tid, &S->team, &S->warp[A->tid >> 5]};
+    env.shfl_slots = S->shfl_slots[A->tid >> 5];
     TeamTwiddles tw;
     load_team_twiddles(S->tables, A->tid, tw);
     if (S->mode == 0) {
@@ -123,6 +136,19 @@ void* worker(void* p) {
                 blind_rotate_team_tm<3, 7>(env, S->sm_tm2, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
             else
                 blind_rotate_team_tm<2, 10>(env, S->sm_tm2, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
+        }
+    } else if (S->mode == 8) {
+        std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
+        env.tm = tmem.data();
+        env.sums_col = 64 * (A->tid % 4);
+        tm_store_twiddles<TeamSmemTm2S>(env, tw);
+        for (int64_t g = 0; g < S->count; ++g) {
+            PbsJob job{(int32_t)g, -1, 0, 1, 0};
+            int32_t* u = S->u_out + (size_t)g * (kN + 1);
+            if (S->L == 3 && S->Bgbit == 7)
+                blind_rotate_team_tm<3, 7>(env, S->sm_tm2s, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
+            else
+                blind_rotate_team_tm<2, 10>(env, S->sm_tm2s, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
         }
     } else if (S->mode == 5) {
         std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
@@ -370,6 +396,18 @@ int peba1_emu_bootstrap_woks_tm2(int L, int Bgbit, int n, const double* bkfft, c
     if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
     Shared* S = new Shared();
     S->mode = 6; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
+    S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+// TeamSmemTm2S: two exchange buffers, inner exchange by warp shuffles (kernel_variant 10)
+int peba1_emu_bootstrap_woks_tm2s(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                                  int64_t count) {
+    if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
+    Shared* S = new Shared();
+    S->mode = 8; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
     S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
     int rc = run(S);
     delete S;

@@ -179,6 +179,10 @@ struct DevEnvTm {
     }
     __device__ __forceinline__ void team_sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kTeam) : "memory"); }
     __device__ __forceinline__ void warp_sync() const { __syncwarp(); }
+    // a complex double to / from the lane whose index differs in `mask` (lane8_transpose, blind_rotate_tm.cuh)
+    __device__ __forceinline__ double2 shfl_xor_c(double2 v, int mask) const {
+        return make_double2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+    }
     __device__ __forceinline__ int32_t ldg(const int32_t* p) const { return __ldg(p); }
     __device__ __forceinline__ double2 ldg2(const double2* p) const { return __ldg(p); }
     __device__ __forceinline__ void tmem_ld4(int col, uint32_t (&w)[4]) const { tmem_ld_x4(tm_base + (uint32_t)col, w); }
@@ -949,11 +953,11 @@ struct peba1_cuda_ctx {
     int narrow_two_buffers = 0;  // 1: the narrow shapes (fixed grids of 1..8 teams) run on TeamSmemTm2 as well (not measured yet)
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int64_t ks_split = -1;   // CTAs per ciphertext in the keyswitch of a narrow level: -1 by batch size, 0 never, else fixed (power of 2)
-    int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..9 are the
+    int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..10 are the
                              // measured alternatives
     int64_t wide_max_batch = -1;  // >= 0: batches up to this size use the low-latency kernel; -1: the measured rule
     int tmk_stagger_ns = 0;       // variant 4: start-up delay per team index
-    int64_t pair_min_batch = -1;  // variants 3..8 below this batch size fall back to variant 1's shapes; -1 = one full wave
+    int64_t pair_min_batch = -1;  // variants 3..10 below this batch size fall back to variant 1's shapes; -1 = one full wave
     int64_t max_pbs_per_launch = 1 << 18;
     // stats
     bool timing = false;
@@ -1086,6 +1090,18 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
         const unsigned grid = std::min((unsigned)((count + kTeamsTm - 1) / kTeamsTm), (unsigned)c->sm_count);
         auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTm2>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
+        return 0;
+    }
+    if (c->kernel_variant == 10 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
+        // variant 8 with the inner exchange of every transform done by warp shuffles (TeamSmemTm2S)
+        const size_t smem = sizeof(TeamSmemTm2S) * (size_t)kTeamsTm;
+        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+        const unsigned grid = std::min((unsigned)((count + kTeamsTm - 1) / kTeamsTm), (unsigned)c->sm_count);
+        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTm2S>;
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
         return 0;
@@ -1316,7 +1332,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
-    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 9 ? atoi(v) : 1;  // tuning aid
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 10 ? atoi(v) : 1;  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev0));
@@ -1839,7 +1855,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 9) return fail(PEBA1_EINVAL, "kernel_variant must be 0..9");
+        if (value < 0 || value > 10) return fail(PEBA1_EINVAL, "kernel_variant must be 0..10");
         c->kernel_variant = (int)value;
         return 0;
     }
