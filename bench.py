@@ -415,7 +415,9 @@ def main():
                      "note": "dominant kernel = blind rotation (FP64 vector pipe; neither hbm nor tensor applies). "
                              "achieved = 162,570,240 flop/PBS x PBS per launch / CUDA-event time of the launch; peak = "
                              "DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); traffic = "
-                             "DRAM bytes per launch from profiles/r1zz_pbs_kernel_tm_final_ncu.txt (the key stays L2-resident)"},
+                             "DRAM bytes per launch from profiles/r1zz_pbs_kernel_tm_final_ncu.txt (the key stays L2-resident; "
+                             "captured on the one-exchange-buffer instantiation of the same kernel, which reads and "
+                             "writes the same global data)"},
         "roofline_keyswitch": {"bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak,
                                "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"),
