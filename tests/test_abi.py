@@ -86,3 +86,16 @@ def test_host_library_exports_every_declared_function():
     assert len(declared) > 60
     missing = [d for d in sorted(declared) if d not in exported and not any(d in e for e in exported if e.startswith("_Z"))]
     assert not missing, missing
+
+
+def test_plain_c_caller_fails_loudly_without_a_device():
+    """A C program that binds nothing but include/peba1_cuda.h (scripts/ubench/kbench.c, the Python-free bench harness)
+    links against the library and, without a device, stops at peba1_cuda_create with the library's own message."""
+    import subprocess
+    L = P.load_library()
+    if L.peba1_cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "peba1_b200", "csrc"),
+                           "../../scripts/ubench/kbench_bin"])
+    r = subprocess.run([os.path.join(ROOT, "scripts", "ubench", "kbench_bin"), "batch=8"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr and r.stdout == ""
