@@ -26,6 +26,8 @@ def test_recorded_gpu_and_oracle_checksums_agree():
         if case.startswith("_") or v["oracle"] is None:
             continue
         assert v["gpu"] == v["oracle"], case
+        if v.get("oracle_exact") is not None:   # the exact-integer form of the oracle on the same workload
+            assert v["gpu"] == v["oracle_exact"], case
 
 
 def test_oracle_reproduces_the_gpu_checksum_of_a_narrow_level():
