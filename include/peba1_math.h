@@ -52,10 +52,15 @@ uint64_t Function_g_clear(uint64_t result_b, uint64_t r0, uint64_t r1, const int
 #ifdef __cplusplus
 extern "C" {
 #endif
+void peba1_math_add1bit(LweSample* result, LweSample* a, LweSample* b, LweSample* carry, const TFheGateBootstrappingCloudKeySet* bk);
 void peba1_math_add(LweSample* result, LweSample* a, LweSample* b, LweSample* carry, int bitsize, const TFheGateBootstrappingCloudKeySet* bk);
 void peba1_math_twos_complement(LweSample* result, LweSample* a, int bitsize, const TFheGateBootstrappingCloudKeySet* bk);
 void peba1_math_abs(LweSample* result, LweSample* a, int bitsize, const TFheGateBootstrappingCloudKeySet* bk);
 void peba1_math_sub(LweSample* result, LweSample* a, LweSample* b, int bitsize, const TFheGateBootstrappingCloudKeySet* bk);
+void peba1_math_shift_left(LweSample* result, LweSample* a, int bitsize, int n, const TFheGateBootstrappingCloudKeySet* bk);
+void peba1_math_shift_right(LweSample* result, LweSample* a, int bitsize, int n, const TFheGateBootstrappingCloudKeySet* bk);
+void peba1_math_shift_left_nr(LweSample* a, int bitsize, int n, const TFheGateBootstrappingCloudKeySet* bk);
+void peba1_math_compare_bit(LweSample* result, const LweSample* a, const LweSample* b, const LweSample* lsb_carry, LweSample* tmp, const TFheGateBootstrappingCloudKeySet* bk);
 /* `width` = 0 reproduces the reference (23, valid for bitsize <= 12); otherwise the product width, e.g. 3*bitsize-1 */
 void peba1_math_multiply(LweSample* result, LweSample* a, LweSample* b, int bitsize, int width, const TFheGateBootstrappingCloudKeySet* bk);
 void peba1_math_minimum(LweSample* result, LweSample* bit, const LweSample* a, const LweSample* b, int nb_bits, const TFheGateBootstrappingCloudKeySet* bk);

@@ -296,6 +296,7 @@ void bootsADD1bit(LweSample* result, LweSample* a, LweSample* b, LweSample* carr
     s.store(result);
     c.store(carry);
 }
+void peba1_math_add1bit(LweSample* r, LweSample* a, LweSample* b, LweSample* c, const TFheGateBootstrappingCloudKeySet* bk) { bootsADD1bit(r, a, b, c, bk); }
 
 void bootsADDNbit(LweSample* result, LweSample* a, LweSample* b, LweSample* carry, const int bitsize, const TFheGateBootstrappingCloudKeySet* bk) {
     RoutineScope scope(bk);
@@ -343,6 +344,9 @@ void bootsShiftRight(LweSample* result, LweSample* a, const int bitsize, const i
 void bootsShiftLeftNR(LweSample* a, const int bitsize, const int n, const TFheGateBootstrappingCloudKeySet* bk) {
     bootsShiftLeft(a, a, bitsize, n, bk);
 }
+void peba1_math_shift_left(LweSample* r, LweSample* a, int bits, int n, const TFheGateBootstrappingCloudKeySet* bk) { bootsShiftLeft(r, a, bits, n, bk); }
+void peba1_math_shift_right(LweSample* r, LweSample* a, int bits, int n, const TFheGateBootstrappingCloudKeySet* bk) { bootsShiftRight(r, a, bits, n, bk); }
+void peba1_math_shift_left_nr(LweSample* a, int bits, int n, const TFheGateBootstrappingCloudKeySet* bk) { bootsShiftLeftNR(a, bits, n, bk); }
 
 void peba1_math_multiply(LweSample* result, LweSample* a, LweSample* b, int bitsize, int width, const TFheGateBootstrappingCloudKeySet* bk) {
     RoutineScope scope(bk);
@@ -364,6 +368,7 @@ void compare_bit(LweSample* result, const LweSample* a, const LweSample* b, cons
     eq.store(tmp);
     r.store(result);
 }
+void peba1_math_compare_bit(LweSample* r, const LweSample* a, const LweSample* b, const LweSample* lsb_carry, LweSample* tmp, const TFheGateBootstrappingCloudKeySet* bk) { compare_bit(r, a, b, lsb_carry, tmp, bk); }
 
 void minimum(LweSample* result, LweSample* bit, const LweSample* a, const LweSample* b, const int nb_bits, const TFheGateBootstrappingCloudKeySet* bk) {
     RoutineScope scope(bk);
