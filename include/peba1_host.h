@@ -74,7 +74,16 @@ void peba1_sample_get_words(const LweSample* sample, int32_t* words); /* as _get
 void peba1_sample_set(LweSample* sample, const int32_t* words);
 LweSample* peba1_sample_at(LweSample* array, int32_t index); /* &array[index] for bindings */
 
-/* Deterministic key generation (new_random_gate_bootstrapping_secret_keyset uses the global generator). */
+/* RANDOMNESS.  Key bits, masks and noise come from ChaCha20 (host/chacha_rng.hpp).  The process-wide generator behind
+   new_random_gate_bootstrapping_secret_keyset and bootsSymEncrypt is keyed with 256 bits from getrandom() at first use
+   (upstream's default engine is unseeded and the reference never seeds it: a faithful copy of that would give every
+   process the same secret key); tfhe_random_generator_setSeed makes it deterministic, as upstream's hook does.
+   The functions below that take a `seed` are DETERMINISTIC BY REQUEST — tests and benchmarks; a 64-bit seed cannot carry
+   128-bit security. */
+/* one ChaCha20 block (8 x 64 bits) for known-answer tests: key[8], 64-bit block counter (state words 12-13), 64-bit
+   stream id (state words 14-15) */
+void peba1_host_chacha_block(const uint32_t key[8], uint64_t block, uint64_t stream, uint64_t out[8]);
+/* Deterministic key generation (new_random_gate_bootstrapping_secret_keyset uses the process-wide generator). */
 TFheGateBootstrappingSecretKeySet* peba1_new_secret_keyset_seeded(const TFheGateBootstrappingParameterSet* params, uint64_t seed);
 /* A keyset around caller-provided key arrays (copied): lwe_key[n], tlwe_key[N] may be NULL for a cloud-only use. */
 TFheGateBootstrappingSecretKeySet* peba1_new_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params,

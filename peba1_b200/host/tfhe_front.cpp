@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/tfhe/tfhe.h"
+#include "chacha_rng.hpp"
 #include "recorder.hpp"
 
 namespace peba1 {
@@ -484,8 +485,20 @@ void sample_assign(LweSample* s, Handle h) {
 void note_linear() { g_stats.linear++; }
 
 // ------------------------------------------------------------------------------------------------ randomness
-// One global generator like upstream (std::default_random_engine there; never seeded by the reference).
-static std::mt19937_64 g_rng(0x5eba1ULL);
+// One process-wide generator like upstream — but a CSPRNG (ChaCha20, chacha_rng.hpp) keyed from the OS entropy pool at
+// first use: upstream's default engine is unseeded and the reference never calls tfhe_random_generator_setSeed
+// (SURVEY.md §8b), which would give every process the same, publicly derivable keys.  setSeed makes it deterministic.
+static ChaChaRng g_rng_state;
+static bool g_rng_keyed = false;
+static ChaChaRng& global_rng() {  // callers hold g_mu
+    if (!g_rng_keyed) {
+        uint32_t key[8];
+        if (!ChaChaRng::os_key(key)) die("cannot read the OS entropy pool (getrandom): refusing to generate predictable keys");
+        g_rng_state = ChaChaRng(key, 0);
+        g_rng_keyed = true;
+    }
+    return g_rng_state;
+}
 
 static inline int32_t double_to_torus32(double d) {  // fractional part of d, scaled to 2^32
     return (int32_t)(int64_t)((d - (double)(int64_t)d) * 4294967296.0);
@@ -514,23 +527,24 @@ static void lwe_encrypt(Rng& rng, const int32_t* key, int n, uint32_t message, d
 // LWE key, ring key, keyswitch key (noise recentred, digit-0 rows noiseless zeros), n TGSW
 // encryptions of the LWE key bits.  Rows are independent, so they are generated on all host cores with per-row
 // generators derived from the master seed (deterministic for a given seed, independent of the thread count).
-static void generate_keys(peba1_key_material* km, uint64_t seed) {
+// All randomness of one key set comes from ONE 256-bit ChaCha20 key; the streams below (master, keyswitch noise, one
+// per key row) are nonces under it.
+static void generate_keys(peba1_key_material* km, const uint32_t key256[8]) {
     const TFheGateBootstrappingParameterSet& p = km->params;
     const int n = p.n, N = p.N, l = p.l, t = p.ks_t, base = 1 << p.ks_basebit, rows = (p.k + 1) * l;
-    std::mt19937_64 master(seed);
+    ChaChaRng master(key256, 0);
     km->lwe_key.resize(n);
     km->tlwe_key.resize(N);
     for (int i = 0; i < n; ++i) km->lwe_key[i] = (int32_t)(master() & 1);
     for (int i = 0; i < N; ++i) km->tlwe_key[i] = (int32_t)(master() & 1);
     km->ksk.assign((size_t)N * t * base * (n + 1), 0);
     km->bk.assign((size_t)n * rows * 2 * N, 0);
-    const uint64_t ks_seed = master(), bk_seed = master();
 
     // keyswitch noises first (their mean is removed, as upstream does), then the samples
     const size_t nks = (size_t)N * t * (base - 1);
     std::vector<double> noise(nks);
     {
-        std::mt19937_64 r(ks_seed);
+        ChaChaRng r(key256, 1);
         std::normal_distribution<double> dist(0.0, p.ks_stdev);
         double mean = 0;
         for (double& x : noise) { x = dist(r); mean += x; }
@@ -545,7 +559,7 @@ static void generate_keys(peba1_key_material* km, uint64_t seed) {
         for (auto& x : th) x.join();
     };
     parallel_for(N, [&](int i) {
-        std::mt19937_64 r(ks_seed ^ (0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1)));
+        ChaChaRng r(key256, 2 + (uint64_t)i);
         for (int j = 0; j < t; ++j)
             for (int h = 1; h < base; ++h) {
                 int32_t* ct = km->ksk.data() + (((size_t)i * t + j) * base + h) * (size_t)(n + 1);
@@ -564,7 +578,7 @@ static void generate_keys(peba1_key_material* km, uint64_t seed) {
     std::vector<int> ones;
     for (int m = 0; m < N; ++m) if (km->tlwe_key[m]) ones.push_back(m);
     parallel_for(n * rows, [&](int ir) {
-        std::mt19937_64 r(bk_seed ^ (0xD1B54A32D192ED03ULL * (uint64_t)(ir + 1)));
+        ChaChaRng r(key256, 2 + (uint64_t)N + (uint64_t)ir);
         uint32_t* a = (uint32_t*)km->bk.data() + ((size_t)ir * 2 + 0) * (size_t)N;
         uint32_t* b = (uint32_t*)km->bk.data() + ((size_t)ir * 2 + 1) * (size_t)N;
         for (int j = 0; j < N; ++j) b[j] = gaussian32(r, 0, p.bk_stdev);
@@ -627,12 +641,23 @@ TFheGateBootstrappingSecretKeySet* peba1_new_secret_keyset_seeded(const TFheGate
     if (!params) die("null parameter set");
     auto* km = new peba1_key_material();
     km->params = *params;
-    generate_keys(km, seed);
+    uint32_t key[8];
+    ChaChaRng::expand_seed(seed, key);  // deterministic: tests and benchmarks only (include/peba1_host.h)
+    generate_keys(km, key);
     return wrap_keyset(km);
 }
 TFheGateBootstrappingSecretKeySet* new_random_gate_bootstrapping_secret_keyset(const TFheGateBootstrappingParameterSet* params) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    return peba1_new_secret_keyset_seeded(params, g_rng());
+    if (!params) die("null parameter set");
+    uint32_t key[8];
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_mu);
+        ChaChaRng& g = global_rng();
+        for (int i = 0; i < 4; ++i) { const uint64_t v = g(); key[2 * i] = (uint32_t)v; key[2 * i + 1] = (uint32_t)(v >> 32); }
+    }
+    auto* km = new peba1_key_material();
+    km->params = *params;
+    generate_keys(km, key);
+    return wrap_keyset(km);
 }
 TFheGateBootstrappingSecretKeySet* peba1_new_keyset_from_arrays(const TFheGateBootstrappingParameterSet* params, const int32_t* lwe_key,
                                                                 const int32_t* tlwe_key, const int32_t* bk, const int32_t* ksk) {
@@ -716,7 +741,7 @@ void bootsSymEncrypt(LweSample* result, int32_t message, const TFheGateBootstrap
     const int n = key->params->n;
     std::vector<int32_t> w((size_t)n + 1);
     const uint32_t mu = mod_switch_to_torus32(1, 8);
-    lwe_encrypt(g_rng, key->lwe_key, n, message ? mu : 0u - mu, key->params->ks_stdev, w.data());
+    lwe_encrypt(global_rng(), key->lwe_key, n, message ? mu : 0u - mu, key->params->ks_stdev, w.data());
     peba1_sample_set(result, w.data());
     (void)n;
 }
@@ -776,8 +801,12 @@ void bootsMUX(LweSample* r, const LweSample* a, const LweSample* b, const LweSam
 
 void tfhe_random_generator_setSeed(uint32_t* values, int32_t size) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
-    std::seed_seq seq(values, values + (size > 0 ? size : 0));
-    g_rng.seed(seq);
+    // upstream's hook: from here on the process-wide generator is deterministic (key = the values, absorbed 8 words at a
+    // time).  The reference never calls it; tests do.
+    uint32_t key[8] = {0x5eba1u, 0, 0, 0, 0, 0, 0, 0};
+    for (int32_t i = 0; i < size; ++i) key[i & 7] = key[i & 7] * 0x9E3779B1u + values[i] + (uint32_t)i;
+    g_rng_state = ChaChaRng(key, 0);
+    g_rng_keyed = true;
 }
 
 // ------------------------------------------------------------------------------------------------ extensions
@@ -897,7 +926,7 @@ const int32_t* peba1_keyset_ksk(const TFheGateBootstrappingCloudKeySet* bk) { re
 void peba1_encrypt_bits(const TFheGateBootstrappingSecretKeySet* key, const int32_t* bits, int64_t count, uint64_t seed, int32_t* words) {
     const int n = key->params->n;
     const uint32_t mu = mod_switch_to_torus32(1, 8);
-    std::mt19937_64 r(seed);
+    ChaChaRng r = ChaChaRng::from_seed(seed, 0x656e63);  // explicit seed: deterministic by request
     for (int64_t i = 0; i < count; ++i)
         lwe_encrypt(r, key->lwe_key, n, bits[i] ? mu : 0u - mu, key->params->ks_stdev, words + (size_t)i * (n + 1));
 }
@@ -909,5 +938,11 @@ void peba1_decrypt_words(const TFheGateBootstrappingSecretKeySet* key, const int
     }
 }
 void* peba1_cuda_context_of(const TFheGateBootstrappingCloudKeySet* bk) { return engine_of(bk)->ctx; }
+
+void peba1_host_chacha_block(const uint32_t key[8], uint64_t block, uint64_t stream, uint64_t out[8]) {
+    ChaChaRng r(key, stream);
+    r.seek(block);
+    for (int i = 0; i < 8; ++i) out[i] = r();
+}
 
 }  // extern "C"
