@@ -97,6 +97,11 @@ int peba1_cuda_download(peba1_cuda_ctx* ctx, int64_t first_slot, int64_t count, 
 /* scattered slots */
 int peba1_cuda_upload_slots(peba1_cuda_ctx* ctx, const int64_t* slots, int64_t count, const int32_t* host);
 int peba1_cuda_download_slots(peba1_cuda_ctx* ctx, const int64_t* slots, int64_t count, int32_t* host);
+/* slots[i] (or first_slot + i when slots is NULL) <- sample i of a dense DEVICE buffer of count*(n+1) words, e.g. what an
+   NCCL broadcast or scatter delivered: no bounce through host memory.  Asynchronous on the context stream when slots is
+   NULL; d_words must stay valid until the copy has run. */
+int peba1_cuda_upload_slots_device(peba1_cuda_ctx* ctx, const int64_t* slots, int64_t first_slot, int64_t count,
+                                   const int32_t* d_words);
 
 /* Device-side encryption of `count` bits (what bootsSymEncrypt, src/main.cpp:64, does per bit):
    slot slots[i] (or first_slot + i when slots is NULL) <- LWE encryption of bits[i] under lwe_key (n words, 0/1) with
@@ -106,13 +111,17 @@ int peba1_cuda_encrypt_bits(peba1_cuda_ctx* ctx, const int32_t* lwe_key, const i
                             int64_t first_slot, int64_t count, int64_t index0, uint64_t seed, double sigma);
 
 /* One circuit level: `count` independent gates, executed as one blind-rotation launch (K0+K1) and one
-   keyswitch launch (K2).  Asynchronous on the context stream. */
+   keyswitch launch (K2).  Asynchronous on the context stream.  An output slot may equal an input slot of the same
+   level (every bootstrap reads before any keyswitch writes).  A level of more than max_pbs_per_launch bootstraps
+   (option, default 2^18) runs as several launch pairs in sequence; if a later pair would read a slot an earlier pair
+   of the same call writes, the call is refused with PEBA1_EINVAL instead of computing a chunk-size-dependent result. */
 int peba1_cuda_gates(peba1_cuda_ctx* ctx, const peba1_gate* gates, int64_t count);
 /* Convenience: the same op for all gates over slot arrays (in2 may be NULL unless op is MUX). */
 int peba1_cuda_gate_batch(peba1_cuda_ctx* ctx, int32_t op, const int64_t* in0, const int64_t* in1,
                           const int64_t* in2, const int64_t* out, int64_t count);
 /* End-to-end form with HOST buffers (count*(n+1) words each): upload, run, download, synchronise.
-   This is what a per-gate `boots*` caller maps to when it owns host ciphertexts. */
+   This is what a per-gate `boots*` caller maps to when it owns host ciphertexts.  It works on private device rows:
+   no slot of the ciphertext pool is read or written (peba1_cuda_keyswitch_host likewise). */
 int peba1_cuda_gate_batch_host(peba1_cuda_ctx* ctx, int32_t op, const int32_t* ca, const int32_t* cb,
                                const int32_t* cc, int32_t* out, int64_t count);
 /* bootsNOT / bootsCOPY / bootsCONSTANT on device slots: out = sign*in + (0, cst); in < 0 means absent. */
@@ -123,6 +132,14 @@ int peba1_cuda_linear(peba1_cuda_ctx* ctx, const int64_t* in, const int32_t* sig
    copied to host): bootstrap without keyswitch (in: count*(n+1) -> out: count*(N+1)) and keyswitch alone. */
 int peba1_cuda_bootstrap_woks_host(peba1_cuda_ctx* ctx, const int32_t* in, int32_t* out_extracted, int64_t count);
 int peba1_cuda_keyswitch_host(peba1_cuda_ctx* ctx, const int32_t* in_extracted, int32_t* out, int64_t count);
+
+/* Per-level device times without a sync per level: between _begin and _end every launch pair of peba1_cuda_gates is
+   bracketed by CUDA events on the context stream; _end waits for the stream and returns, per launch pair, the gates,
+   the bootstraps and the milliseconds of the blind rotation and of the keyswitch (at most `capacity` entries are
+   written; *entries = how many there were). */
+int peba1_cuda_level_log_begin(peba1_cuda_ctx* ctx);
+int peba1_cuda_level_log_end(peba1_cuda_ctx* ctx, int64_t* gates, int64_t* pbs, float* blind_rotate_ms,
+                             float* keyswitch_ms, int64_t capacity, int64_t* entries);
 
 /* Instrumentation. */
 typedef struct {

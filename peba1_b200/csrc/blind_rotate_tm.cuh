@@ -31,11 +31,11 @@ constexpr int kTmBk = 336;      // shared-key variant: 2 row buffers x 64 cells,
 // Shared memory of one team in this version: ONE cross-team exchange buffer (two barriers per transform instead of
 // double buffering) so that 8 teams fit: 8 KB + 8 KB + 8 KB + 1.25 KB = 25.25 KB per team.
 struct __align__(16) TeamSmemTm {
-    static constexpr bool kAliased = false, kDouble = false, kShfl = false;
+    static constexpr bool kAliased = false, kDouble = false, kShfl = false, kClear = true, kXTm = false;
     static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;  // tensor-memory columns (8 teams: 4 x 64 sums)
     // [320,384): decomposition input, 16 columns per warp group; [384,512): the thread's own accumulator words, 32 per
     // warp group (see blind_rotate_team_tm).  The zero block of the other layouts is not needed: the sums are cleared.
-    static constexpr int kTv = 320, kOwn = 384;
+    static constexpr int kTv = 320, kOwn = 384, kX = 0;
     double2  ex1[kM];
     double2  ex2[kM];
     int32_t  acc[2][kN];
@@ -51,9 +51,9 @@ struct __align__(16) TeamSmemTm {
 // [64 hi, 64 hi + 64) there, in both exchanges, and the eight threads of a region sit in one warp: the hazards between
 // the two uses are warp-local (__syncwarp), only the "buffer free" signal moves to after the LAST read of a transform.
 struct __align__(16) TeamSmemTm1 {
-    static constexpr bool kAliased = true, kDouble = false, kShfl = false;
+    static constexpr bool kAliased = true, kDouble = false, kShfl = false, kClear = false, kXTm = false;
     static constexpr int kTw1 = 320, kTw2 = 352, kZero = 384;  // 10 teams: 5 x 64 columns of sums come first
-    static constexpr int kTv = 400, kOwn = -1;   // no columns left for the own-words copy
+    static constexpr int kTv = 400, kOwn = -1, kX = 0;   // no columns left for the own-words copy
     double2  ex1[kM];
     int32_t  acc[2][kN];
     uint16_t bara[640];
@@ -68,9 +68,9 @@ struct __align__(16) TeamSmemTm1 {
 // transforms after it was read, and the team barrier of the transform in between separates the two: a thread passes that
 // barrier only when every thread of the team has arrived at it, i.e. has finished the reads of the transform before.
 struct __align__(16) TeamSmemTm2 {
-    static constexpr bool kAliased = true, kDouble = true, kShfl = false;
+    static constexpr bool kAliased = true, kDouble = true, kShfl = false, kClear = true, kXTm = false;
     static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;
-    static constexpr int kTv = 320, kOwn = 384;
+    static constexpr int kTv = 320, kOwn = 384, kX = 0;
     double2  ex[2][kM];
     int32_t  acc[2][kN];
     uint16_t bara[640];
@@ -88,6 +88,26 @@ struct __align__(16) TeamSmemTm2 {
 // arithmetic, same words.  kernel_variant 10; not measured yet (written after the round's GPU budget was spent).
 struct __align__(16) TeamSmemTm2S : TeamSmemTm2 {
     static constexpr bool kShfl = true;
+};
+
+// The CROSS-TEAM exchange of every transform through TENSOR MEMORY instead of shared memory (kXTm): a thread stores its 8
+// complex values with tcgen05.st.32x32b and the team reads them back with tcgen05.ld.16x256b, whose fragment layout
+// transposes two lane bits against the index of the 64-bit unit inside a 256-bit group (probed:
+// scripts/ubench/tmem_xchg_probe.cu) — none of it touches the LSU / L1 data pipe, which is this kernel's busiest.  The
+// inner exchange stays in shared memory (one warp-local 8 KB buffer).  Tensor-memory columns: [0,256) sums, [256,320)
+// twiddles, [320,384) decomposition input, [384,512) exchange (32 per warp group); the thread-own accumulator copies go
+// back to shared memory.
+struct __align__(16) TeamSmemTmX {
+    static constexpr bool kAliased = true, kDouble = false, kShfl = false, kClear = true, kXTm = true;
+    static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;
+    static constexpr int kTv = 320, kOwn = -1, kX = 384;
+    double2  ex[kM];
+    int32_t  acc[2][kN];
+    uint16_t bara[640];
+    unsigned long long ex1_free;  // unused
+    unsigned long long pad_;
+    PEBA1_HD double2* e1(int) { return ex; }
+    PEBA1_HD double2* e2(int) { return ex; }
 };
 
 // In-place transposition x[j] of lane l  <->  x[l] of lane j over the 8 lanes that share tid >> 3 (lo = tid & 7).
@@ -160,22 +180,47 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
     for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
     radix8<false>(x);
     env.tmem_wait_ld();
+    const int hi = tid >> 3, lo = tid & 7;
+    if constexpr (SM::kXTm) {
+        uint32_t v[32];
+#pragma unroll
+        for (int k0 = 0; k0 < 8; ++k0)
+            c_to_words(cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3])), v[4 * k0], v[4 * k0 + 1],
+                       v[4 * k0 + 2], v[4 * k0 + 3]);
+        env.xtm_exchange(v);
+        env.tmem_ld32(SM::kTw2, w);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) x[b] = words_to_c(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
+    } else {
     if (!SM::kDouble) env.ex1_acquire();  // every reader of the previous transform's ex1 is done (split-phase)
 #pragma unroll
     for (int k0 = 0; k0 < 8; ++k0)
         ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
     env.tmem_ld32(SM::kTw2, w);  // in flight across the barrier, the loads and the second pass
     env.team_sync();
-    const int hi = tid >> 3, lo = tid & 7;
 #pragma unroll
     for (int b = 0; b < 8; ++b) x[b] = ex1[64 * hi + 8 * b + lo];
     if (!SM::kAliased && !SM::kDouble) env.ex1_release();
+    }
     radix8<false>(x);
     env.tmem_wait_ld();
 #if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 2  /* what-if build: no inner exchange in the forward transform */
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
 #else
+#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 4
+    if constexpr (SM::kXTm) {
+        uint32_t v[32];
+        c_to_words(x[0], v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1)
+            c_to_words(cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3])), v[4 * k1], v[4 * k1 + 1],
+                       v[4 * k1 + 2], v[4 * k1 + 3]);
+        env.xtm_inner(v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = words_to_c(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    } else
+#endif
     if (SM::kShfl) {
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
@@ -191,7 +236,7 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
         for (int c = 0; c < 8; ++c) x[c] = ex2[64 * hi + 8 * lo + (c ^ lo)];
     }
 #endif
-    if (SM::kAliased && !SM::kDouble) env.ex1_release();
+    if (SM::kAliased && !SM::kDouble && !SM::kXTm) env.ex1_release();
     radix8<false>(x);
 }
 
@@ -206,6 +251,20 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
     env.tmem_ld32(SM::kTw2, w);
     radix8<true>(x);
     env.tmem_wait_ld();
+#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 4
+    if constexpr (SM::kXTm) {
+        uint32_t v[32];
+        c_to_words(x[0], v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int c = 1; c < 8; ++c)
+            c_to_words(cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3])), v[4 * c], v[4 * c + 1],
+                       v[4 * c + 2], v[4 * c + 3]);
+        env.tmem_ld32(SM::kTw1, w);
+        env.xtm_inner(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) x[k1] = words_to_c(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+    } else
+#endif
     if (SM::kShfl) {
 #pragma unroll
         for (int c = 1; c < 8; ++c) x[c] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
@@ -213,6 +272,7 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
         lane8_transpose(env, x, lo);
     } else {
         if (SM::kDouble) {}                        // a fresh buffer: nobody reads it any more (see TeamSmemTm2)
+        else if (SM::kXTm) env.warp_sync();        // the buffer only carries the warp-local inner exchange
         else if (SM::kAliased) env.ex1_acquire();  // the previous transform's cross-team readers of this region are done
         else env.warp_sync();                      // previous readers of ex2 are done
         ex2[64 * hi + 8 * lo + lo] = x[0];
@@ -225,6 +285,16 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
         for (int k1 = 0; k1 < 8; ++k1) x[k1] = ex2[64 * hi + 8 * k1 + (lo ^ k1)];
     }
     radix8<true>(x);
+    if constexpr (SM::kXTm) {
+        uint32_t v[32];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) c_to_words(x[b], v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
+        env.xtm_exchange(v);  // its tcgen05.wait::ld also covers the twiddle load above
+#pragma unroll
+        for (int k0 = 0; k0 < 8; ++k0)
+            x[k0] = cmul_conj(words_to_c(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]),
+                              words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
+    } else {
     if (SM::kShfl) {}                     // kDouble layout, inner exchange not in memory: a fresh buffer
     else if (SM::kAliased) env.warp_sync();    // the region's readers above are done before it is rewritten
     else env.ex1_acquire();               // previous readers of ex1 are done
@@ -236,6 +306,7 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
     for (int k0 = 0; k0 < 8; ++k0)
         x[k0] = cmul_conj(ex1[64 * k0 + tid], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
     if (!SM::kDouble) env.ex1_release();
+    }
     radix8<true>(x);
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul_conj(x[a], w32(a));
@@ -295,6 +366,8 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
         if (SM::kOwn >= 0) {
             env.tmem_st16(env.own_col, zero);
             env.tmem_st16(env.own_col + 16, own);
+        }
+        if (SM::kClear) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) env.tmem_st16(sums + 16 * q, zero);  // the MAC accumulators start every step at 0
         }
@@ -358,10 +431,10 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
             // Software pipeline: the accumulators and key values of chunk q+1 are in flight while chunk q is
             // multiplied.  Row 0 reads its accumulators from the zero block (no branch, no register clearing).
             const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
-            if (SM::kOwn >= 0 || r > 0) env.tmem_wait_st();  // the previous row's (or the clearing) stores have landed
+            if (SM::kClear || r > 0) env.tmem_wait_st();  // the previous row's (or the clearing) stores have landed
             uint32_t w0[16], w1[16];
             double2 b0[4], b1[4];
-            const int zsel = (SM::kOwn >= 0 || r > 0) ? 1 : 0;  // layouts with a zero block read row 0's accumulators there
+            const int zsel = (SM::kClear || r > 0) ? 1 : 0;  // layouts with a zero block read row 0's accumulators there
 #define PEBA1_CHUNK_COL(q) (zsel ? sums + 32 * ((q) >> 1) + 16 * ((q) & 1) : SM::kZero)
 #if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 1  /* what-if build (scripts/ablate.sh): no key loads */
 #define PEBA1_CHUNK_LDG(q, b)                                                                              \
@@ -404,7 +477,7 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
         for (int c = 0; c < 2; ++c) {
             double2 s[8];
             tm_load8(env, sums + 32 * c, s);
-            if (SM::kOwn >= 0) {  // clear the column for the next step
+            if (SM::kClear) {  // clear the column for the next step
                 uint32_t zero[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) zero[k] = 0u;
@@ -438,303 +511,6 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
     for (int j = tid; j < kN; j += kTeam)
         u_out[j] = (j == 0) ? sm.acc[0][0] : (int32_t)(0u - (uint32_t)sm.acc[0][kN - j]);
     if (tid == 0) u_out[kN] = sm.acc[1][0];
-    env.team_sync();
-}
-
-// Register-accumulator variant of blind_rotate_team_tm for 6 teams per SM (12 warps, up to 168 registers): the MAC
-// accumulators stay in registers for the whole step (no tcgen05.ld/st per row and none of the register moves ptxas wraps
-// around them), twiddles and the decomposition input stay in tensor memory.  Measured basis: 6 teams per SM deliver the
-// same throughput as 8 with the tensor-memory MAC (one wave: 8.3 ms for 888 vs 10.9 ms for 1,184).
-template <int L, int BGBIT, class Env, class SM>
-PEBA1_HD void blind_rotate_team_tmr(Env& env, SM& sm, const double2* __restrict__ bkfft, int n,
-                                   const int32_t* __restrict__ pool, int64_t pool_stride, PbsJob job,
-                                   int32_t* __restrict__ u_out) {
-    constexpr int ROWS = 2 * L;
-    constexpr uint32_t HALF_BG = 1u << (BGBIT - 1);
-    constexpr uint32_t MASK_BG = (1u << BGBIT) - 1;
-    uint32_t offset = 0;
-#pragma unroll
-    for (int p = 1; p <= L; ++p) offset += HALF_BG << (32 - p * BGBIT);
-    const int tid = env.tid;
-    const int sums = env.sums_col;  // kTmSums + 64 * (warp / 4)
-
-    // ---- prologue + mod-switch (identical to blind_rotate_team)
-    for (int w = tid; w <= n; w += kTeam) {
-        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
-    }
-    env.team_sync();
-    {
-        const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);
-        const int32_t mu = 1 << 29;
-        for (int j = tid; j < kN; j += kTeam) {
-            const int idx = (j - rot) & (2 * kN - 1);
-            sm.acc[0][j] = 0;
-            sm.acc[1][j] = (idx & kN) ? -mu : mu;
-        }
-    }
-    env.team_sync();
-
-    for (int i = 0; i < n; ++i) {
-        const int abar = sm.bara[i];
-        if (abar == 0) continue;
-        double2 sum0[8], sum1[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { sum0[q] = make_double2(0.0, 0.0); sum1[q] = make_double2(0.0, 0.0); }
-#ifdef PEBA1_TV_IN_REGS
-        uint32_t tv[16];
-#endif
-#pragma unroll 1
-        for (int r = 0; r < ROWS; ++r) {
-            const int poly = r >= L ? 1 : 0;
-            const int p = r - poly * L;
-#ifndef PEBA1_TV_IN_REGS  /* the default; -DPEBA1_TV_IN_REGS rebuilds the r1f kernel for comparison */
-            // The rotated differences feed L digit levels.  Held in registers across the transforms they cost 16
-            // registers and push the kernel into spilling (LDL/STL = 6 % of its L1 wavefronts); parked in tensor
-            // memory between the levels they cost one store and L-1 loads per polynomial.
-            uint32_t tv[16];
-            if (p == 0) {
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
-                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
-                }
-                env.tmem_st16(env.tv_col, tv);
-            } else {
-                env.tmem_wait_st();
-                env.tmem_ld16(env.tv_col, tv);
-                env.tmem_wait_ld();
-            }
-#else
-            if (p == 0) {
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
-                    tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
-                }
-            }
-#endif
-            const int shift = 32 - (p + 1) * BGBIT;
-            double2 x[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-                x[a] = make_double2(digit2d((tv[a] >> shift) & MASK_BG, HALF_BG), digit2d((tv[8 + a] >> shift) & MASK_BG, HALF_BG));
-            team_fft_forward_tm(env, x, sm);
-            // pointwise MAC against BK_i row r, accumulators in registers (6 teams per SM leave 168 registers per thread)
-            const double2* bk = bkfft + bkfft_index(ROWS, i, r, 0, 0, tid);
-            // chunk q = (column q >> 1, bins 4 (q & 1) ..): the key values of chunk q+1 are requested before chunk q is
-            // multiplied (the same software pipeline as the tensor-memory MAC)
-            double2 b0[4], b1[4];
-#define PEBA1_RLDG(q, b)                                                                                   \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e)                                                          \
-        b[e] = env.ldg2(bk + (size_t)(2 * (4 * ((q) & 1) + e) + ((q) >> 1)) * 64);
-#define PEBA1_RMAC(q, b)                                                                                   \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
-        if ((q) >> 1) cfma(sum1[4 * ((q) & 1) + e], x[4 * ((q) & 1) + e], b[e]);                           \
-        else cfma(sum0[4 * ((q) & 1) + e], x[4 * ((q) & 1) + e], b[e]);                                    \
-    }
-            PEBA1_RLDG(0, b0)
-            PEBA1_RLDG(1, b1)
-            PEBA1_RMAC(0, b0)
-            PEBA1_RLDG(2, b0)
-            PEBA1_RMAC(1, b1)
-            PEBA1_RLDG(3, b1)
-            PEBA1_RMAC(2, b0)
-            PEBA1_RMAC(3, b1)
-#undef PEBA1_RLDG
-#undef PEBA1_RMAC
-        }
-        // inverse transforms and accumulator update (round to nearest, wrap mod 2^32)
-        team_fft_inverse_tm(env, sum0, sm);
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            sm.acc[0][64 * a + tid] = (int32_t)((uint32_t)sm.acc[0][64 * a + tid] + d2u_rn(sum0[a].x));
-            sm.acc[0][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[0][64 * a + tid + 512] + d2u_rn(sum0[a].y));
-        }
-        team_fft_inverse_tm(env, sum1, sm);
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            sm.acc[1][64 * a + tid] = (int32_t)((uint32_t)sm.acc[1][64 * a + tid] + d2u_rn(sum1[a].x));
-            sm.acc[1][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[1][64 * a + tid + 512] + d2u_rn(sum1[a].y));
-        }
-        env.team_sync();
-    }
-
-    for (int j = tid; j < kN; j += kTeam)
-        u_out[j] = (j == 0) ? sm.acc[0][0] : (int32_t)(0u - (uint32_t)sm.acc[0][kN - j]);
-    if (tid == 0) u_out[kN] = sm.acc[1][0];
-    env.team_sync();
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// Shared-key variant.  In blind_rotate_team_tm every team streams the whole key row (16 KB) from L2 through the L1
-// data pipe for itself (ncu r1f: L1 hit rate 15 %, key loads = 23 points of the 78 % L1 pipe utilisation, 6.5 TB/s
-// of L2->SM traffic).  The four teams whose warps share a tensor-memory lane quarter (teams t, t+2, t+4, t+6) hold,
-// lane for lane, the same thread index, hence need the very same key values.  Here they form a GROUP: for each row
-// each team loads ONE quarter of the row (4 values per thread, issued before its transform so the L2 latency is
-// hidden), publishes it in tensor memory, and after a group barrier all four read the whole row from there.  Key
-// traffic through L1/L2 drops 4x.  Price: the group advances roughly in step (split-phase mbarrier per row buffer,
-// two buffers), and a team whose step is void (abar == 0) or that has no job still walks the rows as a producer.
-template <int L, int BGBIT, class Env>
-PEBA1_HD void blind_rotate_team_tmsh(Env& env, TeamSmemTm& sm, const double2* __restrict__ bkfft, int n,
-                                     const int32_t* __restrict__ pool, int64_t pool_stride, PbsJob job, bool live,
-                                     int32_t* __restrict__ u_out) {
-    constexpr int ROWS = 2 * L;
-    constexpr uint32_t HALF_BG = 1u << (BGBIT - 1);
-    constexpr uint32_t MASK_BG = (1u << BGBIT) - 1;
-    uint32_t offset = 0;
-#pragma unroll
-    for (int p = 1; p <= L; ++p) offset += HALF_BG << (32 - p * BGBIT);
-    const int tid = env.tid;
-    const int sums = env.sums_col;
-    const int myq = env.chunk_id;  // which quarter of every key row this team fetches: q = (column c, half)
-
-    for (int w = tid; w <= n; w += kTeam) {
-        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
-    }
-    env.team_sync();
-    {
-        const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);
-        const int32_t mu = 1 << 29;
-        for (int j = tid; j < kN; j += kTeam) {
-            const int idx = (j - rot) & (2 * kN - 1);
-            sm.acc[0][j] = 0;
-            sm.acc[1][j] = (idx & kN) ? -mu : mu;
-        }
-    }
-    env.team_sync();
-
-    // Row s = i*ROWS + r of the key is published (by all four teams, a quarter each) into buffer s & 1 and announced
-    // on the split-phase barrier of that buffer: a team ARRIVES right after publishing its quarter of row s+1 (end of
-    // its row s) and WAITS only just before its MAC of row s+1, i.e. one transform later, so the group tolerates about
-    // one transform of skew instead of meeting at every row.  Overwriting buffer (s+1)&1 is safe: a team gets past its
-    // wait for row s only after every team arrived for row s, which each does after its MAC of row s-1 (the last
-    // reader of that buffer).
-    const int total_rows = n * ROWS;
-    {
-        const double2* bk = bkfft + bkfft_index(ROWS, 0, 0, 0, 0, tid);
-        uint32_t w[16];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const double2 v = env.ldg2(bk + (size_t)(2 * (4 * (myq & 1) + e) + (myq >> 1)) * 64);
-            c_to_words(v, w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);
-        }
-        env.tmem_st16(kTmBk + 16 * myq, w);
-        env.tmem_wait_st();
-        env.group_arrive(0);
-    }
-    int srow = 0;
-    for (int i = 0; i < n; ++i) {
-        const int abar = sm.bara[i];
-        const bool work = abar != 0;  // team-uniform; a void step still produces its share of the key rows
-        uint32_t tv[16];
-#pragma unroll 1
-        for (int r = 0; r < ROWS; ++r, ++srow) {
-            // 1. my quarter of the NEXT key row: in flight during this row's transform
-            const bool more = srow + 1 < total_rows;
-            const int ni = r + 1 < ROWS ? i : i + 1, nr = r + 1 < ROWS ? r + 1 : 0;
-            double2 mine[4];
-            if (more) {
-                const double2* bkn = bkfft + bkfft_index(ROWS, ni, nr, 0, 0, tid);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) mine[e] = env.ldg2(bkn + (size_t)(2 * (4 * (myq & 1) + e) + (myq >> 1)) * 64);
-            }
-            // 2. decompose + forward transform
-            double2 x[8];
-            if (work) {
-                const int poly = r >= L ? 1 : 0;
-                const int p = r - poly * L;
-                if (p == 0) {
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) {
-                        tv[a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid, abar) + offset;
-                        tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
-                    }
-                }
-                const int shift = 32 - (p + 1) * BGBIT;
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    const int32_t dr = (int32_t)((tv[a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
-                    const int32_t di = (int32_t)((tv[8 + a] >> shift) & MASK_BG) - (int32_t)HALF_BG;
-                    x[a] = make_double2(i2d(dr), i2d(di));
-                }
-                team_fft_forward_tm(env, x, sm);
-            }
-            // 3. row s is complete in tensor memory once every team has arrived for it
-            const int buf = kTmBk + 64 * (srow & 1);
-            env.group_wait(srow & 1, (srow >> 1) & 1);
-            // 4. pointwise MAC, accumulators and key both from tensor memory, chunk q+1 in flight during chunk q
-            if (work) {
-                if (r > 0) env.tmem_wait_st();  // the previous row's accumulator stores have landed
-                uint32_t w0[16], w1[16], k0[16], k1[16];
-                const int zsel = r > 0 ? 1 : 0;
-#define PEBA1_CHUNK_COL(q) (zsel ? sums + 16 * (q) : kTmZero)
-#define PEBA1_CHUNK_MAC(q, w, k)                                                                           \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                                        \
-        double2 sacc = words_to_c(w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                      \
-        cfma(sacc, x[4 * ((q) & 1) + e], words_to_c(k[4 * e], k[4 * e + 1], k[4 * e + 2], k[4 * e + 3]));   \
-        c_to_words(sacc, w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);                               \
-    }                                                                                                      \
-    env.tmem_st16(sums + 16 * (q), w);
-                env.tmem_ld16(PEBA1_CHUNK_COL(0), w0);
-                env.tmem_ld16(buf, k0);
-                env.tmem_wait_ld();
-                env.tmem_ld16(PEBA1_CHUNK_COL(1), w1);
-                env.tmem_ld16(buf + 16, k1);
-                PEBA1_CHUNK_MAC(0, w0, k0)
-                env.tmem_wait_ld();
-                env.tmem_ld16(PEBA1_CHUNK_COL(2), w0);
-                env.tmem_ld16(buf + 32, k0);
-                PEBA1_CHUNK_MAC(1, w1, k1)
-                env.tmem_wait_ld();
-                env.tmem_ld16(PEBA1_CHUNK_COL(3), w1);
-                env.tmem_ld16(buf + 48, k1);
-                PEBA1_CHUNK_MAC(2, w0, k0)
-                env.tmem_wait_ld();
-                PEBA1_CHUNK_MAC(3, w1, k1)
-#undef PEBA1_CHUNK_COL
-#undef PEBA1_CHUNK_MAC
-            }
-            // 5. publish my quarter of row s+1 and announce it
-            if (more) {
-                uint32_t w[16];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) c_to_words(mine[e], w[4 * e], w[4 * e + 1], w[4 * e + 2], w[4 * e + 3]);
-                env.tmem_st16(kTmBk + 64 * ((srow + 1) & 1) + 16 * myq, w);
-                env.tmem_wait_st();
-                env.group_arrive((srow + 1) & 1);
-            }
-        }
-        if (work) {
-            env.tmem_wait_st();
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                double2 s[8];
-                tm_load8(env, sums + 32 * c, s);
-                team_fft_inverse_tm(env, s, sm);
-#pragma unroll
-                for (int a = 0; a < 8; ++a) {
-                    sm.acc[c][64 * a + tid] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid] + d2u_rn(s[a].x));
-                    sm.acc[c][64 * a + tid + 512] = (int32_t)((uint32_t)sm.acc[c][64 * a + tid + 512] + d2u_rn(s[a].y));
-                }
-            }
-            env.team_sync();
-        }
-    }
-
-    if (live) {
-        for (int j = tid; j < kN; j += kTeam)
-            u_out[j] = (j == 0) ? sm.acc[0][0] : (int32_t)(0u - (uint32_t)sm.acc[0][kN - j]);
-        if (tid == 0) u_out[kN] = sm.acc[1][0];
-    }
     env.team_sync();
 }
 

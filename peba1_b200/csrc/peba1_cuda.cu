@@ -30,8 +30,11 @@
 
 #include "blind_rotate.cuh"
 #include "blind_rotate_tm.cuh"
+#ifdef PEBA1_ALL_VARIANTS  // measured alternatives that lost: `make VARIANTS=all`
+#include "blind_rotate_tm_variants.cuh"
 #include "blind_rotate_pair.cuh"
 #include "blind_rotate_tmk.cuh"
+#endif
 #include "blind_rotate_wide.cuh"
 #include "twiddles_host.h"
 
@@ -139,6 +142,54 @@ struct DevEnvTm {
     int tv_col = 0;           // 16 tensor-memory columns where the decomposition input waits between digit levels
     int own_col = 0;          // 16 tensor-memory columns with this thread's own words of the body accumulator
     int xpar = 0;             // which exchange buffer the next transform uses (double-buffered layouts)
+    int x_col = 0;            // kXTm layouts: this warp's 32 exchange columns, and the team partner's
+    int x_peer = 0;
+    int x_half = 0;           // which 16 of a block's 32 columns this warp reads back
+    // Cross-team exchange through tensor memory (TeamSmemTmX): every thread stores its 32 words, the team meets, and each
+    // warp reads 16 columns of its own and of its partner's block in the transposing 16x256b shape.
+    __device__ __forceinline__ void xtm_exchange(uint32_t (&v)[32]) const {
+        team_sync();  // the partner has read what the previous transform left in my columns
+        tmem_st_x32(tm_base + (uint32_t)x_col, v);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        team_sync();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t a = tm_base + (uint32_t)((q & 2 ? x_peer : x_col) + 16 * x_half) + ((uint32_t)(16 * (q & 1)) << 16);
+            asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[8 * q]), "=r"(v[8 * q + 1]), "=r"(v[8 * q + 2]), "=r"(v[8 * q + 3]), "=r"(v[8 * q + 4]),
+                           "=r"(v[8 * q + 5]), "=r"(v[8 * q + 6]), "=r"(v[8 * q + 7])
+                         : "r"(a));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 4
+    // WHAT-IF: the inner exchange as one more tensor-memory trip (two lane bits) plus one shuffle stage (the third bit)
+    __device__ __forceinline__ void xtm_inner(uint32_t (&v)[32]) const {
+        team_sync();  // stands for: the partner is done with my columns
+        tmem_st_x32(tm_base + (uint32_t)x_col, v);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t a = tm_base + (uint32_t)x_col + ((uint32_t)(16 * q) << 16);
+            asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[16 * q]), "=r"(v[16 * q + 1]), "=r"(v[16 * q + 2]), "=r"(v[16 * q + 3]), "=r"(v[16 * q + 4]),
+                           "=r"(v[16 * q + 5]), "=r"(v[16 * q + 6]), "=r"(v[16 * q + 7]), "=r"(v[16 * q + 8]), "=r"(v[16 * q + 9]),
+                           "=r"(v[16 * q + 10]), "=r"(v[16 * q + 11]), "=r"(v[16 * q + 12]), "=r"(v[16 * q + 13]),
+                           "=r"(v[16 * q + 14]), "=r"(v[16 * q + 15])
+                         : "r"(a));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const bool up = (threadIdx.x & 4) != 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {  // one butterfly stage: half of the 32 words change hands
+            const uint32_t out = up ? v[j] : v[16 + j];
+            const uint32_t in = __shfl_xor_sync(0xffffffffu, out, 4);
+            if (up) v[j] = in; else v[16 + j] = in;
+        }
+    }
+#endif
     __device__ __forceinline__ int flip() { const int p = xpar; xpar ^= 1; return p; }
     // Split-phase write-after-read protection of the cross-team exchange buffer: a warp signals as soon as its reads
     // are done, the next writer waits just before writing, one whole transform pass later, so nobody actually blocks.
@@ -197,6 +248,7 @@ struct DevEnvTm {
     __device__ __forceinline__ void tmem_wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 };
 
+#ifdef PEBA1_ALL_VARIANTS
 // Key pipeline producer (see blind_rotate_tmk.cuh): one thread of a dedicated 17th warp.
 // Barriers (8 bytes each, from `bars`): tma_full[3] @0, smem_free[3] @24, tmem_full[4] @48, tmem_free[4] @80.
 __device__ __forceinline__ void mbar_wait_parity(uint32_t addr, uint32_t parity) {
@@ -279,6 +331,7 @@ struct DevEnvTmk : DevEnvTm {
     }
 };
 
+#endif  // PEBA1_ALL_VARIANTS
 __constant__ TwiddleTables c_tables;
 
 // The per-thread twiddles are read ONCE into registers.  They must not be rematerialised from constant memory
@@ -301,6 +354,7 @@ struct __align__(16) KsJob {
     int64_t out_slot;
 };
 
+#ifdef PEBA1_ALL_VARIANTS
 // K0+K1.  One team of 64 threads per bootstrap, TEAMS teams per CTA; job index = blockIdx.x*TEAMS + team.
 template <int L, int BGBIT, int TEAMS>
 __global__ void __launch_bounds__(TEAMS* kTeam, 1)
@@ -318,9 +372,10 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
                                 u_out + g * (int64_t)kUStride);
 }
 
+#endif  // PEBA1_ALL_VARIANTS
 // K0+K1, tensor-memory version: 8 teams (512 threads, 16 warps) per CTA, one CTA per SM, <= 128 registers.
 constexpr int kTeamsTm = 8;
-constexpr int kTeamsTm10 = 10;  // with the single-exchange-buffer layout (TeamSmemTm1): 20 warps, 96 registers
+constexpr int kTeamsTm10 = 10;  // (VARIANTS=all) with the single-exchange-buffer layout (TeamSmemTm1): 20 warps, 96 registers
 template <int L, int BGBIT, int TEAMS, class SM = TeamSmemTm, bool REGACC = false>
 __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     pbs_kernel_tm(const double2* __restrict__ bkfft, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
@@ -349,6 +404,11 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
     env.tv_col = SM::kTv + 16 * (warp >> 2);
     env.own_col = SM::kOwn + 32 * (warp >> 2);
+    if (SM::kXTm) {  // WHAT-IF wiring (the partner sits in another lane quarter here): costs right, data wrong
+        env.x_col = SM::kX + 32 * (warp >> 2);
+        env.x_peer = SM::kX + 32 * ((warp >> 2) ^ 1);
+        env.x_half = warp & 1;
+    }
     if ((warp >> 2) == 0) {  // one warp per lane quarter publishes the per-thread twiddles
         TeamTwiddles tw;
 #pragma unroll
@@ -376,10 +436,12 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
             const int64_t g = next_job[team];
             env.team_sync();
             if (g >= count) break;
-            if (REGACC)
+#ifdef PEBA1_ALL_VARIANTS
+            if constexpr (REGACC)
                 blind_rotate_team_tmr<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
                                                 u_out + g * (int64_t)kUStride);
             else
+#endif
                 blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
                                                u_out + g * (int64_t)kUStride);
         }
@@ -390,6 +452,7 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_alloc_base));
 }
 
+#ifdef PEBA1_ALL_VARIANTS
 // K0+K1, shared-key tensor-memory version (blind_rotate_team_tmsh): as pbs_kernel_tm, plus the even teams and the odd
 // teams each form a group that fetches every key row once and shares it through tensor memory.
 template <int L, int BGBIT>
@@ -569,6 +632,7 @@ __global__ void __launch_bounds__(kTmkThreads, 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm_alloc_base));
 }
 
+#endif  // PEBA1_ALL_VARIANTS
 // Device-side encryption: synthetic gallery / benchmark inputs generated where they are used
 // instead of 2.5 KB per bit over PCIe.  One warp per ciphertext; counter-based generator (Philox4x32-10, keyed by the
 // seed, counter = ciphertext index and word block), so the output depends only on (seed, index), not on the launch
@@ -668,6 +732,8 @@ __global__ void __launch_bounds__(2 * L * kTeam, 1)
         __syncthreads();
         blind_rotate_wide<L, BGBIT>(env, sm, tw, team, bkfft, n, pool, pool_stride, jobs[g], u_out + g * (int64_t)kUStride);
         __syncthreads();  // the shared accumulator is reused by the CTA's next job
+        if (env.tid == 0)  // the next job initialises the barrier again: a live mbarrier must be invalidated first
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&sm.key_full[team])) : "memory");
     }
 }
 
@@ -947,6 +1013,16 @@ struct peba1_cuda_ctx {
     size_t d_stage_cap = 0;
     int32_t* h_stage = nullptr;  // pinned
     size_t h_stage_cap = 0;
+    // private rows of the host-buffer entry points (gate_batch_host, keyswitch_host): same stride as the pool, never
+    // visible to the caller, so those calls leave every pool slot untouched
+    int32_t* hb_pool = nullptr;
+    int64_t hb_slots = 0;
+    cudaEvent_t stream_switch = nullptr;  // orders work across peba1_cuda_set_stream
+    // level log (peba1_cuda_level_log_begin/_end): three events per launch pair, resolved at _end without syncing between
+    bool log_on = false;
+    std::vector<cudaEvent_t> log_ev;
+    std::vector<int64_t> log_gates, log_pbs;
+    size_t log_n = 0;
     // options
     int teams_per_cta = 6;
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
@@ -988,6 +1064,13 @@ int ensure_pinned(void** ptr, size_t* cap, size_t need) {
     return 0;
 }
 
+// temporary device buffer of one call: freed on every return path
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
 int use_device(peba1_cuda_ctx* c) {
     if (!c) return fail(PEBA1_EINVAL, "null context");
     CU(cudaSetDevice(c->device));
@@ -1003,6 +1086,8 @@ bool params_supported(const peba1_cuda_params& p) {
 }
 
 size_t team_smem_bytes(int teams) { return sizeof(TeamSmem) * (size_t)teams; }
+
+#ifdef PEBA1_ALL_VARIANTS
 
 template <int TEAMS>
 int launch_pbs_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
@@ -1023,6 +1108,7 @@ int launch_pbs_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const P
     return 0;
 }
 
+#endif  // PEBA1_ALL_VARIANTS
 template <int L, int BGBIT, int TEAMS, class SM>
 int launch_pbs_tm_ts(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
                      int32_t* u) {
@@ -1043,6 +1129,7 @@ int launch_pbs_tm_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
 template <int L, int BGBIT>
 int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
                     int32_t* u) {
+#ifdef PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 2) {
         const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm;
         const unsigned grid = (unsigned)((count + kTeamsTm - 1) / kTeamsTm);
@@ -1081,6 +1168,7 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, T6 * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
         return 0;
     }
+#endif  // PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 8 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // two alternating exchange buffers without the "buffer free" mbarrier (TeamSmemTm2): what the default does for
@@ -1094,6 +1182,19 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
         return 0;
     }
+    if (c->kernel_variant == 11 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
+        // cross-team exchange of every transform through tensor memory (TeamSmemTmX)
+        const size_t smem = sizeof(TeamSmemTmX) * (size_t)kTeamsTm;
+        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+        const unsigned grid = std::min((unsigned)((count + kTeamsTm - 1) / kTeamsTm), (unsigned)c->sm_count);
+        auto k = pbs_kernel_tm<L, BGBIT, kTeamsTm, TeamSmemTmX>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
+        return 0;
+    }
+#ifdef PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 10 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // variant 8 with the inner exchange of every transform done by warp shuffles (TeamSmemTm2S)
@@ -1106,6 +1207,7 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
         return 0;
     }
+#endif  // PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 7 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // persistent 8-team CTAs on the single cross-team exchange buffer with its "buffer free" mbarrier (TeamSmemTm): the
@@ -1119,6 +1221,7 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
         return 0;
     }
+#ifdef PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 4 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         const size_t smem = sizeof(TeamSmemTm) * (size_t)kTeamsTm + 3 * kKeyHalfBytes;
@@ -1137,6 +1240,7 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, kTeamsPair * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u);
         return 0;
     }
+#endif  // PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 1 && c->tm_teams == 0 && count >= (int64_t)c->sm_count * kTeamsTm) {
         // wide batch (the default path): one persistent 8-team CTA per SM, jobs drawn from a counter, on two alternating
         // exchange buffers (= variant 8).  With the accumulator copies in tensor memory this instantiation has no spills
@@ -1203,6 +1307,7 @@ int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const Pbs
         c->stats.pbs += (uint64_t)count;
         return 0;
     }
+#ifdef PEBA1_ALL_VARIANTS
     switch (c->teams_per_cta) {
         case 1: rc = launch_pbs_t<1>(c, pool, stride, jobs, count, u); break;
         case 2: rc = launch_pbs_t<2>(c, pool, stride, jobs, count, u); break;
@@ -1215,6 +1320,9 @@ int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const Pbs
     if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
     c->stats.pbs += (uint64_t)count;
     return 0;
+#else
+    return fail(PEBA1_EINVAL, "kernel_variant 0 is not compiled into this build (make VARIANTS=all)");
+#endif
 }
 
 int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t count, int32_t* pool) {
@@ -1327,14 +1435,19 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     CU(cudaSetDevice(device));
     peba1_cuda_ctx* c = new (std::nothrow) peba1_cuda_ctx();
     if (!c) return fail(PEBA1_ENOMEM, "out of host memory");
+    struct Guard {  // a failing step below must not leak the context, its stream, events and buffers
+        peba1_cuda_ctx* c;
+        ~Guard() { if (c) { char keep[sizeof g_err]; memcpy(keep, g_err, sizeof keep); peba1_cuda_destroy(c); memcpy(g_err, keep, sizeof keep); } }
+    } guard{c};
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->p = *params;
     c->rows = 2 * params->l;
     c->pool_stride = ((int64_t)params->n + 1 + kPoolPad - 1) / kPoolPad * kPoolPad;
-    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) c->kernel_variant = atoi(v) >= 0 && atoi(v) <= 10 ? atoi(v) : 1;  // tuning aid
+    if (const char* v = getenv("PEBA1_KERNEL_VARIANT")) peba1_cuda_set_option(c, "kernel_variant", atoi(v));  // tuning aid
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CU(cudaEventCreateWithFlags(&c->stream_switch, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
     CU(cudaEventCreate(&c->ev2));
@@ -1347,6 +1460,7 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
     c->ksk_bytes = (size_t)kN * params->ks_t * ((1 << params->ks_basebit) - 1) * c->ksk_stride * sizeof(int32_t);
     CU(cudaMalloc(&c->bkfft, c->bkfft_bytes));
     CU(cudaMalloc(&c->ksk, c->ksk_bytes));
+    guard.c = nullptr;
     *out = c;
     return 0;
 }
@@ -1354,22 +1468,33 @@ int peba1_cuda_create(int device, const peba1_cuda_params* params, peba1_cuda_ct
 int peba1_cuda_destroy(peba1_cuda_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->bkfft); cudaFree(c->ksk); cudaFree(c->pool); cudaFree(c->u); cudaFree(c->d_jobs); cudaFree(c->d_job_counter); cudaFree(c->d_stage);
+    cudaFree(c->hb_pool);
+    for (cudaEvent_t e : c->log_ev) cudaEventDestroy(e);
+    if (c->stream_switch) cudaEventDestroy(c->stream_switch);
     for (int b = 0; b < 2; ++b) {
         cudaFreeHost(c->h_jobs[b]);
         if (c->jobs_copied[b]) cudaEventDestroy(c->jobs_copied[b]);
     }
     cudaFreeHost(c->h_stage);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2);
-    cudaStreamDestroy(c->own_stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
 }
 
 int peba1_cuda_set_stream(peba1_cuda_ctx* c, void* s) {
-    if (!c) return fail(PEBA1_EINVAL, "null context");
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    if (int rc = use_device(c)) return rc;
+    cudaStream_t next = s ? (cudaStream_t)s : c->own_stream;
+    if (next == c->stream) return 0;
+    // work queued on the old stream (launches that still read the job lists, the workspaces, the pool) stays ordered
+    // before whatever the new stream is given
+    CU(cudaEventRecord(c->stream_switch, c->stream));
+    CU(cudaStreamWaitEvent(next, c->stream_switch, 0));
+    c->stream = next;
     return 0;
 }
 
@@ -1384,8 +1509,9 @@ int peba1_cuda_load_bootstrap_key(peba1_cuda_ctx* c, const int32_t* bk_host) {
     if (!bk_host) return fail(PEBA1_EINVAL, "null key");
     const int64_t polys = (int64_t)c->p.n * c->rows * 2;
     const size_t bytes = (size_t)polys * kN * sizeof(int32_t);
-    int32_t* d_bk = nullptr;
-    CU(cudaMalloc(&d_bk, bytes));
+    DevBuf buf;
+    CU(cudaMalloc(&buf.p, bytes));
+    int32_t* d_bk = buf.as<int32_t>();
     CU(cudaMemcpyAsync(d_bk, bk_host, bytes, cudaMemcpyHostToDevice, c->stream));
     constexpr int TEAMS = 4;
     auto k = key_transform_kernel<TEAMS>;
@@ -1394,7 +1520,6 @@ int peba1_cuda_load_bootstrap_key(peba1_cuda_ctx* c, const int32_t* bk_host) {
     CU(cudaGetLastError());
     c->stats.launches++;
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(d_bk));
     c->bk_loaded = true;
     return 0;
 }
@@ -1404,15 +1529,15 @@ int peba1_cuda_load_keyswitch_key(peba1_cuda_ctx* c, const int32_t* ksk_host) {
     if (!ksk_host) return fail(PEBA1_EINVAL, "null key");
     const int base = 1 << c->p.ks_basebit;
     const size_t words = (size_t)kN * c->p.ks_t * base * (c->p.n + 1);
-    int32_t* d_src = nullptr;
-    CU(cudaMalloc(&d_src, words * sizeof(int32_t)));
+    DevBuf buf;
+    CU(cudaMalloc(&buf.p, words * sizeof(int32_t)));
+    int32_t* d_src = buf.as<int32_t>();
     CU(cudaMemcpyAsync(d_src, ksk_host, words * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     const int64_t rows_out = (int64_t)kN * c->p.ks_t * (base - 1);
     ksk_pack_kernel<<<(unsigned)rows_out, 128, 0, c->stream>>>(d_src, c->p.n, base, c->ksk_stride, rows_out, c->ksk);
     CU(cudaGetLastError());
     c->stats.launches++;
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(d_src));
     c->ksk_loaded = true;
     return 0;
 }
@@ -1462,20 +1587,37 @@ int peba1_cuda_pool_info(peba1_cuda_ctx* c, void** device_ptr, int64_t* stride_w
     return 0;
 }
 
-static int check_slots(peba1_cuda_ctx* c, const int64_t* slots, int64_t first, int64_t count) {
+// grows the private rows of the host-buffer entry points (contents need not survive: every call rewrites what it reads)
+static int ensure_hb_rows(peba1_cuda_ctx* c, int64_t slots) {
+    if (slots <= c->hb_slots) return 0;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->hb_pool) CU(cudaFree(c->hb_pool));
+    c->hb_pool = nullptr;
+    c->hb_slots = 0;
+    if (cudaMalloc(&c->hb_pool, (size_t)slots * c->pool_stride * sizeof(int32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PEBA1_ENOMEM, "cannot allocate %lld staging rows for a host-buffer call", (long long)slots);
+    }
+    c->hb_slots = slots;
+    return 0;
+}
+
+static int check_slots(int64_t pool_slots, const int64_t* slots, int64_t first, int64_t count) {
     if (count < 0) return fail(PEBA1_EINVAL, "negative count");
     if (slots) {
         for (int64_t i = 0; i < count; ++i)
-            if (slots[i] < 0 || slots[i] >= c->pool_slots) return fail(PEBA1_EINVAL, "slot %lld outside the pool (%lld slots)", (long long)slots[i], (long long)c->pool_slots);
-    } else if (first < 0 || first + count > c->pool_slots) {
-        return fail(PEBA1_EINVAL, "slot range [%lld, %lld) outside the pool (%lld slots)", (long long)first, (long long)(first + count), (long long)c->pool_slots);
+            if (slots[i] < 0 || slots[i] >= pool_slots) return fail(PEBA1_EINVAL, "slot %lld outside the pool (%lld slots)", (long long)slots[i], (long long)pool_slots);
+    } else if (first < 0 || first + count > pool_slots) {
+        return fail(PEBA1_EINVAL, "slot range [%lld, %lld) outside the pool (%lld slots)", (long long)first, (long long)(first + count), (long long)pool_slots);
     }
     return 0;
 }
 
-static int transfer(peba1_cuda_ctx* c, const int64_t* slots, int64_t first, int64_t count, const int32_t* h_in, int32_t* h_out) {
+// host <-> rows of `pool` (the ciphertext pool, or the private rows of the host-buffer entry points)
+static int transfer(peba1_cuda_ctx* c, int32_t* pool, int64_t pool_slots, const int64_t* slots, int64_t first, int64_t count,
+                    const int32_t* h_in, int32_t* h_out) {
     if (int rc = use_device(c)) return rc;
-    if (int rc = check_slots(c, slots, first, count)) return rc;
+    if (int rc = check_slots(pool_slots, slots, first, count)) return rc;
     if (count == 0) return 0;
     if ((h_in == nullptr) == (h_out == nullptr)) return fail(PEBA1_EINVAL, "null host buffer");
     const int w = c->p.n + 1;
@@ -1492,9 +1634,9 @@ static int transfer(peba1_cuda_ctx* c, const int64_t* slots, int64_t first, int6
         }
         if (h_in) {
             CU(cudaMemcpyAsync(c->d_stage, h_in + (size_t)off * w, bytes, cudaMemcpyHostToDevice, c->stream));
-            scatter_kernel<<<(unsigned)m, 128, 0, c->stream>>>(c->pool, c->pool_stride, c->p.n, d_slots, first + off, c->d_stage);
+            scatter_kernel<<<(unsigned)m, 128, 0, c->stream>>>(pool, c->pool_stride, c->p.n, d_slots, first + off, c->d_stage);
         } else {
-            gather_kernel<<<(unsigned)m, 128, 0, c->stream>>>(c->pool, c->pool_stride, c->p.n, d_slots, first + off, c->d_stage);
+            gather_kernel<<<(unsigned)m, 128, 0, c->stream>>>(pool, c->pool_stride, c->p.n, d_slots, first + off, c->d_stage);
             CU(cudaMemcpyAsync(h_out + (size_t)off * w, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
         }
         CU(cudaGetLastError());
@@ -1504,18 +1646,47 @@ static int transfer(peba1_cuda_ctx* c, const int64_t* slots, int64_t first, int6
     return 0;
 }
 
-int peba1_cuda_upload(peba1_cuda_ctx* c, int64_t first, int64_t count, const int32_t* host) { return transfer(c, nullptr, first, count, host, nullptr); }
-int peba1_cuda_download(peba1_cuda_ctx* c, int64_t first, int64_t count, int32_t* host) { return transfer(c, nullptr, first, count, nullptr, host); }
+int peba1_cuda_upload(peba1_cuda_ctx* c, int64_t first, int64_t count, const int32_t* host) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    return transfer(c, c->pool, c->pool_slots, nullptr, first, count, host, nullptr);
+}
+int peba1_cuda_download(peba1_cuda_ctx* c, int64_t first, int64_t count, int32_t* host) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    return transfer(c, c->pool, c->pool_slots, nullptr, first, count, nullptr, host);
+}
 int peba1_cuda_upload_slots(peba1_cuda_ctx* c, const int64_t* slots, int64_t count, const int32_t* host) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
     if (!slots) return fail(PEBA1_EINVAL, "null slots");
-    return transfer(c, slots, 0, count, host, nullptr);
+    return transfer(c, c->pool, c->pool_slots, slots, 0, count, host, nullptr);
 }
 int peba1_cuda_download_slots(peba1_cuda_ctx* c, const int64_t* slots, int64_t count, int32_t* host) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
     if (!slots) return fail(PEBA1_EINVAL, "null slots");
-    return transfer(c, slots, 0, count, nullptr, host);
+    return transfer(c, c->pool, c->pool_slots, slots, 0, count, nullptr, host);
+}
+// slots[i] <- the i-th dense sample (n+1 words) of a DEVICE buffer, e.g. what an NCCL broadcast / scatter delivered:
+// no bounce through host memory.  Asynchronous on the context stream; `d_words` must stay valid until it has run.
+int peba1_cuda_upload_slots_device(peba1_cuda_ctx* c, const int64_t* slots, int64_t first_slot, int64_t count, const int32_t* d_words) {
+    if (int rc = use_device(c)) return rc;
+    if (int rc = check_slots(c->pool_slots, slots, first_slot, count)) return rc;
+    if (count == 0) return 0;
+    if (!d_words) return fail(PEBA1_EINVAL, "null device buffer");
+    int64_t* d_slots = nullptr;
+    if (slots) {
+        CU(cudaStreamSynchronize(c->stream));  // d_jobs may still be read by queued launches
+        if (int rc = ensure_dev(&c->d_jobs, &c->d_jobs_cap, (size_t)count * sizeof(int64_t))) return rc;
+        d_slots = (int64_t*)c->d_jobs;
+        CU(cudaMemcpyAsync(d_slots, slots, (size_t)count * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    scatter_kernel<<<(unsigned)count, 128, 0, c->stream>>>(c->pool, c->pool_stride, c->p.n, d_slots, first_slot, d_words);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    if (slots) CU(cudaStreamSynchronize(c->stream));  // the pageable slot list has been consumed
+    return 0;
 }
 
-int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) {
+// one circuit level on the rows of `pool` (the ciphertext pool, or the private rows of the host-buffer entry points)
+static int run_gates(peba1_cuda_ctx* c, int32_t* pool, int64_t pool_slots, const peba1_gate* gates, int64_t count) {
     if (int rc = use_device(c)) return rc;
     if (count < 0 || (count > 0 && !gates)) return fail(PEBA1_EINVAL, "bad gate list");
     if (!c->bk_loaded || !c->ksk_loaded) return fail(PEBA1_ENOKEY, "keys are not loaded");
@@ -1527,11 +1698,45 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
         for (int q = 0; q < nin; ++q) {
             if (g.flags & PEBA1_IN_CONST(q)) {
                 if (g.in[q] != 0 && g.in[q] != 1) return fail(PEBA1_EINVAL, "gate %lld: constant operand must be 0 or 1", (long long)i);
-            } else if (g.in[q] < 0 || g.in[q] >= c->pool_slots) {
-                return fail(PEBA1_EINVAL, "gate %lld: input slot %lld outside the pool (%lld slots)", (long long)i, (long long)g.in[q], (long long)c->pool_slots);
+            } else if (g.in[q] < 0 || g.in[q] >= pool_slots) {
+                return fail(PEBA1_EINVAL, "gate %lld: input slot %lld outside the pool (%lld slots)", (long long)i, (long long)g.in[q], (long long)pool_slots);
             }
         }
-        if (g.out < 0 || g.out >= c->pool_slots) return fail(PEBA1_EINVAL, "gate %lld: output slot %lld outside the pool", (long long)i, (long long)g.out);
+        if (g.out < 0 || g.out >= pool_slots) return fail(PEBA1_EINVAL, "gate %lld: output slot %lld outside the pool", (long long)i, (long long)g.out);
+    }
+    // Level semantics (every bootstrap reads before any keyswitch writes) hold inside ONE launch pair.  A level larger than
+    // max_pbs_per_launch runs as several pairs in sequence: an output slot that a LATER chunk reads would then hand
+    // that chunk the new value, and the result would depend on the chunk size.  Refuse instead of computing it.
+    {
+        int64_t total_pbs = 0;
+        for (int64_t i = 0; i < count; ++i) total_pbs += gates[i].op == PEBA1_OP_MUX ? 2 : 1;
+        if (total_pbs > c->max_pbs_per_launch) {
+            std::vector<int64_t> outs;
+            outs.reserve((size_t)count);
+            int64_t npbs = 0, chunk_start = 0;
+            std::vector<int64_t> earlier;  // sorted outputs of the chunks before the current one
+            for (int64_t i = 0; i < count; ++i) {
+                const peba1_gate& g = gates[i];
+                const int need = g.op == PEBA1_OP_MUX ? 2 : 1;
+                if (i > chunk_start && npbs + need > c->max_pbs_per_launch) {
+                    earlier.insert(earlier.end(), outs.begin(), outs.end());
+                    std::sort(earlier.begin(), earlier.end());
+                    outs.clear();
+                    npbs = 0;
+                    chunk_start = i;
+                }
+                npbs += need;
+                outs.push_back(g.out);
+                if (!earlier.empty()) {
+                    const int nin = g.op >= PEBA1_OP_MUX ? 3 : 2;
+                    for (int q = 0; q < nin; ++q)
+                        if (!(g.flags & PEBA1_IN_CONST(q)) && std::binary_search(earlier.begin(), earlier.end(), g.in[q]))
+                            return fail(PEBA1_EINVAL, "gate %lld reads slot %lld, which an earlier chunk of this level (more than "
+                                        "max_pbs_per_launch = %lld bootstraps) writes: in-place levels must fit one launch",
+                                        (long long)i, (long long)g.in[q], (long long)c->max_pbs_per_launch);
+                }
+            }
+        }
     }
     int64_t done = 0;
     while (done < count) {
@@ -1620,12 +1825,60 @@ int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) 
         CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs[hb], kb_off + kb, cudaMemcpyHostToDevice, c->stream));
         CU(cudaEventRecord(c->jobs_copied[hb], c->stream));
         c->jobs_pending[hb] = true;
-        if (int rc = launch_pbs(c, c->pool, c->pool_stride, (const PbsJob*)c->d_jobs, npbs, c->u)) return rc;
-        if (int rc = launch_ks(c, c->u, (const KsJob*)((char*)c->d_jobs + kb_off), m, c->pool)) return rc;
+        cudaEvent_t* lev = nullptr;
+        if (c->log_on) {
+            while (c->log_ev.size() < 3 * (c->log_n + 1)) {
+                cudaEvent_t e;
+                CU(cudaEventCreate(&e));
+                c->log_ev.push_back(e);
+            }
+            lev = &c->log_ev[3 * c->log_n];
+            c->log_gates.push_back(m);
+            c->log_pbs.push_back(npbs);
+            c->log_n++;
+            CU(cudaEventRecord(lev[0], c->stream));
+        }
+        if (int rc = launch_pbs(c, pool, c->pool_stride, (const PbsJob*)c->d_jobs, npbs, c->u)) return rc;
+        if (lev) CU(cudaEventRecord(lev[1], c->stream));
+        if (int rc = launch_ks(c, c->u, (const KsJob*)((char*)c->d_jobs + kb_off), m, pool)) return rc;
+        if (lev) CU(cudaEventRecord(lev[2], c->stream));
         if (int rc = collect_timing(c, true, true)) return rc;
         done += m;
     }
     return 0;  // asynchronous on the context stream (peba1_cuda_sync, or any download, waits)
+}
+
+int peba1_cuda_gates(peba1_cuda_ctx* c, const peba1_gate* gates, int64_t count) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    return run_gates(c, c->pool, c->pool_slots, gates, count);
+}
+
+// Per-level device times without a sync per level: between _begin and _end every launch pair is bracketed by events on
+// the context stream; _end waits for the stream and resolves them.
+int peba1_cuda_level_log_begin(peba1_cuda_ctx* c) {
+    if (!c) return fail(PEBA1_EINVAL, "null context");
+    c->log_on = true;
+    c->log_n = 0;
+    c->log_gates.clear();
+    c->log_pbs.clear();
+    return 0;
+}
+int peba1_cuda_level_log_end(peba1_cuda_ctx* c, int64_t* gates, int64_t* pbs, float* blind_rotate_ms, float* keyswitch_ms,
+                             int64_t capacity, int64_t* entries) {
+    if (int rc = use_device(c)) return rc;
+    c->log_on = false;
+    CU(cudaStreamSynchronize(c->stream));
+    if (entries) *entries = (int64_t)c->log_n;
+    for (size_t i = 0; i < c->log_n && (int64_t)i < capacity; ++i) {
+        if (gates) gates[i] = c->log_gates[i];
+        if (pbs) pbs[i] = c->log_pbs[i];
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, c->log_ev[3 * i], c->log_ev[3 * i + 1]));
+        CU(cudaEventElapsedTime(&b, c->log_ev[3 * i + 1], c->log_ev[3 * i + 2]));
+        if (blind_rotate_ms) blind_rotate_ms[i] = a;
+        if (keyswitch_ms) keyswitch_ms[i] = b;
+    }
+    return 0;
 }
 
 int peba1_cuda_gate_batch(peba1_cuda_ctx* c, int32_t op, const int64_t* in0, const int64_t* in1, const int64_t* in2, const int64_t* out, int64_t count) {
@@ -1649,10 +1902,11 @@ int peba1_cuda_gate_batch_host(peba1_cuda_ctx* c, int32_t op, const int32_t* ca,
     if (mux && count > 0 && !cc) return fail(PEBA1_EINVAL, "MUX, XOR3 and MAJ3 need three operands");
     if (count == 0) return 0;
     const int nin = mux ? 3 : 2;
-    if (int rc = peba1_cuda_pool_reserve(c, (nin + 1) * count)) return rc;
-    if (int rc = peba1_cuda_upload(c, 0, count, ca)) return rc;
-    if (int rc = peba1_cuda_upload(c, count, count, cb)) return rc;
-    if (mux) if (int rc = peba1_cuda_upload(c, 2 * count, count, cc)) return rc;
+    if (int rc = use_device(c)) return rc;
+    if (int rc = ensure_hb_rows(c, (nin + 1) * count)) return rc;  // private rows: the caller's pool slots stay untouched
+    if (int rc = transfer(c, c->hb_pool, c->hb_slots, nullptr, 0, count, ca, nullptr)) return rc;
+    if (int rc = transfer(c, c->hb_pool, c->hb_slots, nullptr, count, count, cb, nullptr)) return rc;
+    if (mux) if (int rc = transfer(c, c->hb_pool, c->hb_slots, nullptr, 2 * count, count, cc, nullptr)) return rc;
     std::vector<peba1_gate> g((size_t)count);
     for (int64_t i = 0; i < count; ++i) {
         g[i].op = op;
@@ -1662,8 +1916,8 @@ int peba1_cuda_gate_batch_host(peba1_cuda_ctx* c, int32_t op, const int32_t* ca,
         g[i].in[2] = mux ? 2 * count + i : 0;
         g[i].out = nin * count + i;
     }
-    if (int rc = peba1_cuda_gates(c, g.data(), count)) return rc;
-    return peba1_cuda_download(c, nin * count, count, out);
+    if (int rc = run_gates(c, c->hb_pool, c->hb_slots, g.data(), count)) return rc;
+    return transfer(c, c->hb_pool, c->hb_slots, nullptr, nin * count, count, nullptr, out);
 }
 
 int peba1_cuda_linear(peba1_cuda_ctx* c, const int64_t* in, const int32_t* sign, const int32_t* cst, const int64_t* out, int64_t count) {
@@ -1694,12 +1948,13 @@ int peba1_cuda_bootstrap_woks_host(peba1_cuda_ctx* c, const int32_t* in, int32_t
     if (!c->bk_loaded) return fail(PEBA1_ENOKEY, "bootstrapping key is not loaded");
     if (count == 0) return 0;
     const int w = c->p.n + 1;
-    int32_t *d_in = nullptr, *d_u = nullptr, *d_dense = nullptr;
-    PbsJob* d_j = nullptr;
-    CU(cudaMalloc(&d_in, (size_t)count * w * sizeof(int32_t)));
-    CU(cudaMalloc(&d_u, (size_t)count * kUStride * sizeof(int32_t)));
-    CU(cudaMalloc(&d_dense, (size_t)count * (kN + 1) * sizeof(int32_t)));
-    CU(cudaMalloc(&d_j, (size_t)count * sizeof(PbsJob)));
+    DevBuf b_in, b_u, b_dense, b_j;
+    CU(cudaMalloc(&b_in.p, (size_t)count * w * sizeof(int32_t)));
+    CU(cudaMalloc(&b_u.p, (size_t)count * kUStride * sizeof(int32_t)));
+    CU(cudaMalloc(&b_dense.p, (size_t)count * (kN + 1) * sizeof(int32_t)));
+    CU(cudaMalloc(&b_j.p, (size_t)count * sizeof(PbsJob)));
+    int32_t *d_in = b_in.as<int32_t>(), *d_u = b_u.as<int32_t>(), *d_dense = b_dense.as<int32_t>();
+    PbsJob* d_j = b_j.as<PbsJob>();
     std::vector<PbsJob> jobs((size_t)count);
     for (int64_t i = 0; i < count; ++i) jobs[i] = PbsJob{(int32_t)i, -1, 0, 1, 0};
     CU(cudaMemcpyAsync(d_in, in, (size_t)count * w * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -1710,7 +1965,6 @@ int peba1_cuda_bootstrap_woks_host(peba1_cuda_ctx* c, const int32_t* in, int32_t
     c->stats.launches++;
     CU(cudaMemcpyAsync(out_extracted, d_dense, (size_t)count * (kN + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d_in); cudaFree(d_u); cudaFree(d_dense); cudaFree(d_j);
     return 0;
 }
 
@@ -1719,12 +1973,13 @@ int peba1_cuda_keyswitch_host(peba1_cuda_ctx* c, const int32_t* in_extracted, in
     if (count < 0 || (count > 0 && (!in_extracted || !out))) return fail(PEBA1_EINVAL, "null host buffer");
     if (!c->ksk_loaded) return fail(PEBA1_ENOKEY, "keyswitch key is not loaded");
     if (count == 0) return 0;
-    if (int rc = peba1_cuda_pool_reserve(c, count)) return rc;
-    int32_t *d_u = nullptr, *d_dense = nullptr;
-    KsJob* d_j = nullptr;
-    CU(cudaMalloc(&d_u, (size_t)count * kUStride * sizeof(int32_t)));
-    CU(cudaMalloc(&d_dense, (size_t)count * (kN + 1) * sizeof(int32_t)));
-    CU(cudaMalloc(&d_j, (size_t)count * sizeof(KsJob)));
+    if (int rc = ensure_hb_rows(c, count)) return rc;  // private rows, not the caller's pool
+    DevBuf b_u, b_dense, b_j;
+    CU(cudaMalloc(&b_u.p, (size_t)count * kUStride * sizeof(int32_t)));
+    CU(cudaMalloc(&b_dense.p, (size_t)count * (kN + 1) * sizeof(int32_t)));
+    CU(cudaMalloc(&b_j.p, (size_t)count * sizeof(KsJob)));
+    int32_t *d_u = b_u.as<int32_t>(), *d_dense = b_dense.as<int32_t>();
+    KsJob* d_j = b_j.as<KsJob>();
     std::vector<KsJob> jobs((size_t)count);
     for (int64_t i = 0; i < count; ++i) jobs[i] = KsJob{(int32_t)i, -1, 0, 0, i};
     CU(cudaMemcpyAsync(d_dense, in_extracted, (size_t)count * (kN + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -1733,11 +1988,10 @@ int peba1_cuda_keyswitch_host(peba1_cuda_ctx* c, const int32_t* in_extracted, in
     CU(cudaGetLastError());
     c->stats.launches++;
     if (c->timing) CU(cudaEventRecord(c->ev1, c->stream));
-    if (int rc = launch_ks(c, d_u, d_j, count, c->pool)) return rc;
+    if (int rc = launch_ks(c, d_u, d_j, count, c->hb_pool)) return rc;
     if (int rc = collect_timing(c, false, true)) return rc;
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d_u); cudaFree(d_dense); cudaFree(d_j);
-    return peba1_cuda_download(c, 0, count, out);
+    return transfer(c, c->hb_pool, c->hb_slots, nullptr, 0, count, nullptr, out);
 }
 
 int peba1_cuda_encrypt_bits(peba1_cuda_ctx* c, const int32_t* lwe_key, const int32_t* bits, const int64_t* slots,
@@ -1754,8 +2008,9 @@ int peba1_cuda_encrypt_bits(peba1_cuda_ctx* c, const int32_t* lwe_key, const int
     for (int w = 0; w < c->p.n; ++w)
         if (lwe_key[w]) mask[w >> 5] |= 1u << (w & 31);
     const size_t bytes = sizeof mask + (size_t)count * sizeof(int32_t) + 8 + (slots ? (size_t)count * sizeof(int64_t) : 0);
-    unsigned char* d = nullptr;
-    CU(cudaMalloc(&d, bytes));
+    DevBuf buf;
+    CU(cudaMalloc(&buf.p, bytes));
+    unsigned char* d = buf.as<unsigned char>();
     CU(cudaMemcpyAsync(d, mask, sizeof mask, cudaMemcpyHostToDevice, c->stream));
     int32_t* d_bits = reinterpret_cast<int32_t*>(d + sizeof mask);
     CU(cudaMemcpyAsync(d_bits, bits, (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
@@ -1771,7 +2026,6 @@ int peba1_cuda_encrypt_bits(peba1_cuda_ctx* c, const int32_t* lwe_key, const int
     CU(cudaGetLastError());
     c->stats.launches++;
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
     return 0;
 }
 
@@ -1795,8 +2049,9 @@ int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* c, double* tflops) {
     if (int rc = use_device(c)) return rc;
     if (!tflops) return fail(PEBA1_EINVAL, "null argument");
     const int threads = 256, blocks = c->sm_count * 8, iters = 1 << 14;
-    double* d = nullptr;
-    CU(cudaMalloc(&d, (size_t)threads * blocks * sizeof(double)));
+    DevBuf buf;
+    CU(cudaMalloc(&buf.p, (size_t)threads * blocks * sizeof(double)));
+    double* d = buf.as<double>();
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         CU(cudaEventRecord(c->ev0, c->stream));
@@ -1807,7 +2062,6 @@ int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* c, double* tflops) {
         CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         if (rep > 0) best = std::min(best, ms);
     }
-    CU(cudaFree(d));
     c->stats.launches += 4;
     *tflops = 2.0 * 8 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;
     return 0;
@@ -1855,7 +2109,12 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 10) return fail(PEBA1_EINVAL, "kernel_variant must be 0..10");
+        if (value < 0 || value > 11) return fail(PEBA1_EINVAL, "kernel_variant must be 0..11");
+#ifndef PEBA1_ALL_VARIANTS
+        if (value != 1 && value != 7 && value != 8 && value != 11)
+            return fail(PEBA1_EINVAL, "kernel_variant %lld lost against the default and is not compiled into this build "
+                                      "(make -C peba1_b200/csrc VARIANTS=all)", (long long)value);
+#endif
         c->kernel_variant = (int)value;
         return 0;
     }

@@ -24,7 +24,8 @@ DECLARED_SYMBOLS = [
     "peba1_cuda_gate_batch_host",
     "peba1_cuda_linear", "peba1_cuda_bootstrap_woks_host", "peba1_cuda_keyswitch_host",
     "peba1_cuda_enable_timing", "peba1_cuda_get_stats", "peba1_cuda_reset_stats",
-    "peba1_cuda_measure_fp64_peak", "peba1_cuda_set_option",
+    "peba1_cuda_measure_fp64_peak", "peba1_cuda_set_option", "peba1_cuda_upload_slots_device",
+    "peba1_cuda_level_log_begin", "peba1_cuda_level_log_end",
 ]
 
 
@@ -111,6 +112,9 @@ def load_library():
     L.peba1_cuda_reset_stats.argtypes = [vp]
     L.peba1_cuda_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.peba1_cuda_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.peba1_cuda_upload_slots_device.argtypes = [vp, i64p, C.c_int64, C.c_int64, vp]
+    L.peba1_cuda_level_log_begin.argtypes = [vp]
+    L.peba1_cuda_level_log_end.argtypes = [vp, i64p, i64p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int64, i64p]
     _lib = L
     return L
 
@@ -210,6 +214,12 @@ class Engine:
         assert cts.shape[0] == slots.size
         self._chk(self.L.peba1_cuda_upload_slots(self.h, _i64(slots), slots.size, _i32(cts.reshape(-1))))
 
+    def upload_slots_device(self, device_ptr: int, count: int, first_slot: int = 0, slots=None):
+        """pool rows <- `count` dense samples of a DEVICE buffer (no host bounce); see peba1_cuda_upload_slots_device."""
+        sl = None if slots is None else np.ascontiguousarray(slots, dtype=np.int64)
+        self._chk(self.L.peba1_cuda_upload_slots_device(self.h, None if sl is None else _i64(sl), first_slot, count,
+                                                        C.c_void_p(device_ptr)))
+
     def download_slots(self, slots) -> np.ndarray:
         slots = np.ascontiguousarray(slots, dtype=np.int64)
         out = np.empty((slots.size, self.words), dtype=np.int32)
@@ -284,6 +294,20 @@ class Engine:
     def enable_timing(self, on: bool = True):
         self._chk(self.L.peba1_cuda_enable_timing(self.h, int(on)))
 
+    def level_log_begin(self):
+        self._chk(self.L.peba1_cuda_level_log_begin(self.h))
+
+    def level_log_end(self, capacity: int = 1 << 16):
+        """-> (gates, pbs, blind_rotate_ms, keyswitch_ms) arrays, one entry per launch pair since level_log_begin"""
+        g, p = np.zeros(capacity, dtype=np.int64), np.zeros(capacity, dtype=np.int64)
+        a, b = np.zeros(capacity, dtype=np.float32), np.zeros(capacity, dtype=np.float32)
+        n = C.c_int64()
+        f32p = C.POINTER(C.c_float)
+        self._chk(self.L.peba1_cuda_level_log_end(self.h, _i64(g), _i64(p), a.ctypes.data_as(f32p), b.ctypes.data_as(f32p),
+                                                  capacity, C.byref(n)))
+        k = min(int(n.value), capacity)
+        return g[:k], p[:k], a[:k], b[:k]
+
     def stats(self) -> Stats:
         s = Stats()
         self._chk(self.L.peba1_cuda_get_stats(self.h, C.byref(s)))
@@ -299,6 +323,11 @@ class Engine:
 
     def set_option(self, name: str, value: int):
         self._chk(self.L.peba1_cuda_set_option(self.h, name.encode(), value))
+
+    def try_variant(self, variant: int) -> bool:
+        """Selects a blind-rotation kernel variant; False when it is not compiled into this build (the measured
+        alternatives that lost are only built with `make -C peba1_b200/csrc VARIANTS=all`)."""
+        return self.L.peba1_cuda_set_option(self.h, b"kernel_variant", variant) == 0
 
 
 def make_gates(op, in0, in1, out, in2=None, flags=0) -> np.ndarray:

@@ -10,6 +10,7 @@
 #include <vector>
 #include "blind_rotate.cuh"
 #include "blind_rotate_tm.cuh"
+#include "blind_rotate_tm_variants.cuh"
 #include "blind_rotate_pair.cuh"
 #include "blind_rotate_tmk.cuh"
 #include "blind_rotate_wide.cuh"

@@ -58,8 +58,6 @@ def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "peba1_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
-                if f == "emu_team.cu":
-                    continue
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "tfhe_oracle" not in txt and "pyoracle" not in txt, os.path.join(dirpath, f)
 

@@ -173,7 +173,9 @@ def test_gpu_full_size_face_match_equals_the_reference(gpu_side, keys):
     assert (side.counters() - c0).tolist() == g["ed/counters"].tolist()
     assert np.array_equal(got, g["ed/words"])
     assert R.bits_value(keys.decrypt(got)[:23]) == int(g["distance"])
-    for tag, verdict in (("ge", 1), ("lt", 0)):
+    # the bit minimum() hands Function_f is "ed > bound" (compare_bit keeps a's bit at the highest differing position,
+    # Math.cpp:259-261): 0 for the bound AT the distance, 1 for the bound just below it — the reference's own words say so
+    for tag, verdict in (("ge", 0), ("lt", 1)):
         eb = R._int_in(side, enc, int(g[f"result_b/{tag}/bound"]), 24, f"bound{int(g[f'result_b/{tag}/bound'])}")
         rb = side.new_array(24)
         side.fn("function_f")(rb, pa, pb, slots, eb, 8, side.cloud)

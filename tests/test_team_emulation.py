@@ -1,5 +1,5 @@
 """CPU test of the very code the blind-rotation kernel runs: csrc/negacyclic_fft.cuh + blind_rotate.cuh are
-__host__ __device__, and csrc/emu_team.cu executes one 64-thread team with CPU threads.  It must reproduce the
+__host__ __device__, and tests/emu/emu_team.cu executes one 64-thread team with CPU threads.  It must reproduce the
 exact-integer oracle word for word (this container has no GPU; the -m gpu tests repeat this on the device)."""
 import ctypes as C
 import os
@@ -9,14 +9,14 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "peba1_b200", "csrc")
+EMU = os.path.join(ROOT, "tests", "emu")
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "gates_seed42.npz")
 
 
 @pytest.fixture(scope="module")
 def emu():
-    subprocess.check_call(["make", "-s", "-C", CSRC, "libpeba1_emu.so"])
-    return C.CDLL(os.path.join(CSRC, "libpeba1_emu.so"))
+    subprocess.check_call(["make", "-s", "-C", EMU, "libpeba1_emu.so"])
+    return C.CDLL(os.path.join(EMU, "libpeba1_emu.so"))
 
 
 @pytest.fixture(scope="module")
