@@ -8,6 +8,14 @@ ciphertexts at TFHE default 128-bit parameters (n=630, N=1024), one batch per GP
 One "step" = one pass of the hot path (gate prologue + blind rotation + sample extraction + keyswitch) over one batch
 whose input ciphertexts are already resident in the device pool.  Prints ONE JSON line (rank 0).
 
+Beside the headline the line carries the other BASELINE configs as legs (all verified by decryption on the rank that
+computed them):
+  face_match_strong   configs[3] shape, FIXED total: 1 probe vs --face-total templates split over the N GPUs, faithful
+                      circuit (every reference gate), host recording + NCCL scatter-free hot loop + all-gather of the
+                      encrypted match bits inside the timed region; with a per-level time histogram by level width
+  circuits            configs[2]: --circuit-instances x ADD8 / ADD16 / MUL8 (Math.cpp:54, :214), instances split over N
+  face_match_mode2/3  the folded circuits, --face-templates per GPU (weak)
+
 `--impl reference` times the CPU implementation of the same path (the oracle port of TFHE's algorithm — the reference's
 own TFHE dependency is neither vendored nor installable here) on the box's host cores.
 """
@@ -30,7 +38,18 @@ KEY_SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this very
 # command at batch 16,384 (profiles/r1zz_pbs_kernel_tm_final_ncu.txt, profiles/r1s_keyswitch_kernel_ncu.txt); reported as
 # roofline.traffic when the run uses that batch, null otherwise.
-NCU_TRAFFIC = {16384: {"blind_rotate": 624066816 + 78354944, "keyswitch": 402676992 + 43154688}}
+NCU_TRAFFIC = {16384: {"blind_rotate": 573091072 + 68749312, "keyswitch": 402676992 + 43154688}}
+NCU_SOURCE = {"blind_rotate": "profiles/r2a_pbs_kernel_tm_TeamSmemTm2_ncu.txt (the shipped default instantiation)",
+              "keyswitch": "profiles/r1s_keyswitch_kernel_ncu.txt"}
+FP64_PEAK_NOMINAL = 148 * 64 * 2 * 1.965e9 / 1e12   # 37.2 TFLOP/s: 148 SMs x 64 DFMA lanes x 2 flop x 1.965 GHz
+
+
+def workload_config(args):
+    """config of BOTH arms (the driver compares the two dicts)."""
+    return {"workload": f"gate-bootstrap microbench (BASELINE configs[1]): batch of {args.batch} boots{args.op} per GPU on "
+                        "random ciphertexts, n=630 N=1024 k=1 l=3 Bgbit=7, keyswitch t=8 base 4",
+            "batch_per_gpu": args.batch, "op": args.op,
+            "l2": "working set per step (inputs, extracted samples, outputs, keys) is 315 MB > 126 MB L2; no explicit flush"}
 
 
 def parse():
@@ -45,7 +64,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-face-match", action="store_true")
     ap.add_argument("--no-other-ops", action="store_true", help="skip the XOR / MUX legs of configs[1]")
-    ap.add_argument("--face-templates", type=int, default=8, help="templates per GPU in the face-match leg (0: skip)")
+    ap.add_argument("--face-templates", type=int, default=8, help="templates per GPU in the folded face-match legs (0: skip)")
+    ap.add_argument("--face-total", type=int, default=64,
+                    help="templates in the fixed-size (strong-scaling) faithful face-match leg, split over the GPUs (0: skip)")
+    ap.add_argument("--circuit-instances", type=int, default=4096,
+                    help="instances of each configs[2] circuit (ADD8 / ADD16 / MUL8), split over the GPUs (0: skip)")
     return ap.parse_args()
 
 
@@ -128,15 +151,11 @@ def run_reference(args):
         "impl": "reference", "metric": "bootstrapped gates/s (PBS/s)", "value": rate, "unit": "PBS/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        # the own arm's workload (same string), of which every step here runs a bounded sample on the host cores
-        "config": {"workload": f"gate-bootstrap microbench (BASELINE configs[1]): batch of {args.batch} boots{args.op} per "
-                               "GPU on random ciphertexts, n=630 N=1024 k=1 l=3 Bgbit=7, keyswitch t=8 base 4",
-                   "batch_per_gpu": args.batch, "op": args.op,
-                   "sample": f"{gates} of the {args.batch} gates per step (a gate's cost does not depend on the batch)",
-                   "batch_per_step": gates},
+        "config": workload_config(args),
         "cpu_baseline": {"value": rate, "unit": "PBS/s", "cores": cores, "kind": "port",
-                         "sample": f"{gates} boots{args.op} gates per step, one gate per thread, oracle FP64-FFT form "
-                                   "(reference's TFHE dependency is not vendored; see DESIGN.md)"},
+                         "sample": f"{gates} of the {args.batch} boots{args.op} gates per step (a gate's cost does not depend on "
+                                   "the batch), one gate per thread, oracle FP64-FFT form (the reference's TFHE dependency is "
+                                   "not vendored; see DESIGN.md)", "batch_per_step": gates},
         "e2e": {"value": rate, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -148,14 +167,57 @@ class _DevPtr:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=0):
-    """Encrypted face matches/s (BASELINE metric, second half): Function_f = 128-dim 8-bit squared distance + 24-bit
-    threshold compare, one probe against `T` templates per GPU (peba1_b200/gallery.py).  Timed: recording + the 377
-    batched levels + the NCCL all-gather of the encrypted match bits; not timed: client-side encryption and scatter."""
+def _max_over_ranks(torch, dist, dev, value):
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _all_true(torch, dist, dev, flag):
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+WIDTH_BUCKETS = (148, 296, 592, 1184, 4736, 1 << 62)   # <= one bootstrap per SM, 2, 4, 8 per SM (one wave), <= 4 waves, more
+
+
+def level_histogram(np, gates, pbs, br_ms, ks_ms):
+    """per-level device times of one pass, grouped by level width (bootstraps per launch)"""
+    out = []
+    lo = 0
+    for hi in WIDTH_BUCKETS:
+        m = (pbs > lo) & (pbs <= hi)
+        if m.any():
+            ms = float(br_ms[m].sum() + ks_ms[m].sum())
+            out.append({"pbs_per_level": f"{lo + 1}..{hi}" if hi < (1 << 62) else f">{lo}", "levels": int(m.sum()),
+                        "pbs": int(pbs[m].sum()), "blind_rotate_ms": float(br_ms[m].sum()), "keyswitch_ms": float(ks_ms[m].sum()),
+                        "share_of_device_time": None, "pbs_per_s": float(pbs[m].sum()) / (ms * 1e-3) if ms > 0 else None})
+        lo = hi
+    total = sum(b["blind_rotate_ms"] + b["keyswitch_ms"] for b in out)
+    for b in out:
+        b["share_of_device_time"] = (b["blind_rotate_ms"] + b["keyswitch_ms"]) / total if total > 0 else None
+    return out
+
+
+def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=0, total=None):
+    """Encrypted face matches/s (BASELINE metric, second half): Function_f (Math.cpp:379) = 128-dim 8-bit squared distance
+    + 24-bit threshold compare, one probe against a gallery (peba1_b200/gallery.py; main.cpp:513-581 for one template).
+    total=None: `--face-templates` per GPU (weak).  total=T: T templates in all, split over the ranks (strong; configs[3]
+    shape at a size that fits the driver's time limit).  Rank 0 is the client (encrypts on the host); probe and bound are
+    NCCL-broadcast, templates NCCL-scattered, and what arrives is bound to pool rows by a device-side scatter.
+    Timed: host recording of every gate + the batched levels + the NCCL all-gather of the encrypted match bits."""
     from peba1_b200 import gallery as G
     from peba1_b200 import tfhe_host as H
     H.load_library().peba1_set_mode(mode)
-    T = args.face_templates
+    if total is None:
+        T = args.face_templates
+    else:
+        if total % world:
+            total += world - total % world
+        T = total // world
     slots, bits, words = 128, 8, ks.words
     dev = f"cuda:{local}"
     bound = 512
@@ -164,7 +226,9 @@ def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=0):
     if rank == 0:
         client = (ks.encrypt(G.bits_of(probe, bits), 501), ks.encrypt(G.bits_of([bound], 24), 502),
                   ks.encrypt(G.bits_of(gal.reshape(-1), bits), 503))
-    probe_w, bound_w, mine_w = G.distribute(dist, rank, world, dev, torch, words, slots, bits, T, client)
+    probe_t, bound_t, mine_t = G.distribute_device(dist, rank, world, dev, torch, words, slots, bits, T, client)
+    vecs = G.device_vectors(ks, mine_t.reshape(-1, words), T, slots, bits)
+    probe_w, bound_w = probe_t.cpu().numpy(), bound_t.cpu().numpy()
 
     def barrier():
         if dist is not None:
@@ -172,20 +236,23 @@ def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=0):
         torch.cuda.synchronize()
     s0 = ks.stats()
     c0 = eng.stats().launches
+    if total is not None:
+        eng.level_log_begin()
     barrier()
     t0 = time.perf_counter()
-    out = G.match_templates(ks, probe_w, bound_w, mine_w, slots, bits)
+    out = G.match_template_arrays(ks, probe_w, bound_w, vecs, slots, bits)
     allout = G.gather_match_bits(dist, world, dev, torch, out)       # encrypted match bits over NVLink
     barrier()
-    dt = time.perf_counter() - t0
-    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dt = float(tt.item())
+    dt = _max_over_ranks(torch, dist, dev, time.perf_counter() - t0)
+    hist = None
+    if total is not None:
+        hist = level_histogram(np, *eng.level_log_end())
     s1 = ks.stats()
     H.load_library().peba1_set_mode(0)
     pbs = int(s1.executed_pbs - s0.executed_pbs)
-    res = {"value": world * T / dt, "unit": "face matches/s", "templates": world * T, "templates_per_gpu": T,
+    res = {"value": world * T / dt, "unit": "face matches/s", "face_matches_per_s": world * T / dt,
+           "templates": world * T, "templates_per_gpu": T,
+           "scaling": "weak" if total is None else "strong (fixed total, split over the GPUs)",
            "circuit_mode": ["faithful (every reference gate bootstrapped; raw-ciphertext parity)",
                             "fold (constant folding + dead-gate elimination; decrypted parity)",
                             "fold + MUX-carry adders (decrypted parity)",
@@ -194,12 +261,72 @@ def face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=0):
            "seconds": dt, "pbs": pbs * world, "pbs_per_match": pbs / max(T, 1), "pbs_per_s": pbs * world / dt,
            "levels": int(s1.levels - s0.levels), "gpu_launches": int(eng.stats().launches - c0),
            "workload": f"Function_f (128-dim 8-bit squared distance + 24-bit threshold), 1 probe vs {world * T} templates, "
-                       "one batch per GPU", "timing": "wall clock incl. host recording, max over ranks"}
+                       f"{T} per GPU in one batch (BASELINE configs[3] shape)",
+           "timing": "wall clock incl. host recording and the all-gather, max over ranks"}
+    if hist is not None:
+        res["level_histogram_rank0"] = hist
+    ok = True
     if rank == 0:
         got = ks.decrypt(allout)
-        res["verified"] = bool(np.array_equal(got, expect))
+        ok = bool(np.array_equal(got, expect))
         res["matches_found"] = int((got == 0).sum())
+    res["verified"] = _all_true(torch, dist, dev, ok)
     return res
+
+
+def circuits_leg(args, ks, eng, dist, rank, world, local, torch, np):
+    """BASELINE configs[2]: `--circuit-instances` independent instances of the 8- and 16-bit ripple-carry adder
+    (bootsADDNbit, Math.cpp:54) and of the 8-bit multiplier (bootsMultiply, Math.cpp:214), every circuit level of all
+    instances in ONE launch pair; instances split over the ranks.  Operands are encrypted on the device; a sample of
+    the results is decrypted and compared with integer arithmetic (main.cpp:320, :456).  Timed: recording + execution."""
+    from peba1_b200 import tfhe_host as H
+    L = H.load_library()
+    dev = f"cuda:{local}"
+    inst = max(1, args.circuit_instances // world)
+    rng = np.random.default_rng(300 + rank)
+    out = {}
+    for name, bits, width in (("ADD8", 8, 9), ("ADD16", 16, 17), ("MUL8", 8, 23)):
+        xs, ys = rng.integers(0, 1 << bits, size=inst), rng.integers(0, 1 << bits, size=inst)
+        A = [ks.new_array(bits) for _ in range(inst)]
+        B = [ks.new_array(bits) for _ in range(inst)]
+        R = [ks.new_array(24 if name == "MUL8" else bits) for _ in range(inst)]
+        Cy = [ks.new_array(1) for _ in range(inst)] if name != "MUL8" else None
+        from peba1_b200.gallery import bits_of
+        ks.encrypt_array_list_device(A, bits, bits_of(xs, bits), 900 + rank)
+        ks.encrypt_array_list_device(B, bits, bits_of(ys, bits), 950 + rank)
+        s0, c0 = ks.stats(), eng.stats().launches
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.peba1_batch_begin()
+        for i in range(inst):
+            if name == "MUL8":
+                L.peba1_math_multiply(R[i], A[i], B[i], bits, 0, ks.cloud)
+            else:
+                L.peba1_math_add(R[i], A[i], B[i], Cy[i], bits, ks.cloud)
+        L.peba1_batch_end()
+        eng.sync()
+        dt = _max_over_ranks(torch, dist, dev, time.perf_counter() - t0)
+        s1 = ks.stats()
+        ok = True
+        for i in range(0, inst, max(1, inst // 32)):                 # a sample of 32 instances, decrypted
+            if name == "MUL8":
+                got = ks.decrypt_int(R[i], 23)
+                ok &= got == int(xs[i]) * int(ys[i])
+            else:
+                got = ks.decrypt_int(R[i], bits) | (ks.decrypt_int(Cy[i], 1) << bits)
+                ok &= got == int(xs[i]) + int(ys[i])
+        for arr, n in [(a, bits) for a in A + B] + [(r, 24 if name == "MUL8" else bits) for r in R] + \
+                ([(c, 1) for c in Cy] if Cy else []):
+            ks.free_array(n, arr)
+        pbs = int(s1.executed_pbs - s0.executed_pbs)
+        out[name] = {"instances": inst * world, "instances_per_gpu": inst, "pbs": pbs * world, "levels": int(s1.levels - s0.levels),
+                     "seconds": dt, "pbs_per_s": pbs * world / dt, "instances_per_s": inst * world / dt,
+                     "gpu_launches": int(eng.stats().launches - c0), "verified": _all_true(torch, dist, dev, bool(ok))}
+    out["workload"] = ("Math.cpp ripple-carry adders and multiplier, every instance batched per circuit level "
+                       "(BASELINE configs[2]); timing = wall clock incl. host recording, max over ranks")
+    return out
 
 
 def main():
@@ -246,28 +373,40 @@ def main():
         dist.broadcast(tb, 0)
         torch.cuda.synchronize()
         eng.keys_mark_loaded()
-    key_note = "host keygen (libpeba1_tfhe) seed 42 on rank 0" + ("; device-format keys NCCL-broadcast" if world > 1 else "")
+    # every rank verifies ITS OWN outputs: the secret LWE key (630 bits) follows the cloud keys, into the replica's
+    # (so far empty) secret-key array.  A deployment never does this — only the client holds it; here the benchmark is
+    # client and server at once, and a rank that computed garbage must not hide behind rank 0's check.
+    if dist is not None:
+        tk = torch.from_numpy(np.ascontiguousarray(ks.lwe_key)).to(f"cuda:{local}")
+        dist.broadcast(tk, 0)
+        if rank != 0:
+            ks.lwe_key[:] = tk.cpu().numpy()
+    key_note = "host keygen (libpeba1_tfhe) seed 42 on rank 0" + (
+        "; device-format cloud keys NCCL-broadcast; secret LWE key broadcast for per-rank verification" if world > 1 else "")
+    dev = f"cuda:{local}"
 
-    # ---- inputs resident in the pool: rank 0 uses real encryptions of random bits (and verifies the decrypted outputs
-    # of the timed batch); the other ranks use random words (the arithmetic is data-independent)
+    # ---- inputs resident in the pool: every rank holds real encryptions of its own random bits (rank 0: host encryption,
+    # which also feeds the host-buffer leg; the others: device-side encryption) and verifies its decrypted outputs
     B = args.batch
     nin = 3 if args.op == "MUX" else 2
     words = p.n + 1
     rng = np.random.default_rng(1000 + rank)
     bits = rng.integers(0, 2, size=(nin, B))
-    if rank == 0:
-        host_in = ks.encrypt(bits.reshape(-1), seed=77).reshape(nin, B, words)
-    else:
-        host_in = rng.integers(-2**31, 2**31, size=(nin, B, words), dtype=np.int64).astype(np.int32)
+    base = 1 << 20                                 # bench slots sit above anything the recorder allocates
+    eng.reserve(base + (nin + 1) * B)
+    host_in = ks.encrypt(bits.reshape(-1), seed=77 + rank).reshape(nin, B, words)
     pinned_in = torch.empty((nin, B, words), dtype=torch.int32).pin_memory()
     pinned_in.numpy()[...] = host_in
     pinned_out = torch.empty((B, words), dtype=torch.int32).pin_memory()
-    base = 1 << 20                                 # bench slots sit above anything the recorder allocates
-    eng.reserve(base + (nin + 1) * B)
-    eng.upload(base, host_in.reshape(-1, words))
+    if rank == 0:
+        eng.upload(base, host_in.reshape(-1, words))
+    else:
+        eng.encrypt_bits(ks.lwe_key, bits.reshape(-1), base, seed=77 + rank)
     idx = base + np.arange(B)
     gates = make_gates(args.op, idx, B + idx, nin * B + idx, in2=(2 * B + idx) if args.op == "MUX" else None)
     pbs_per_step = B * (2 if args.op == "MUX" else 1)
+    a, b = bits[0], bits[1]
+    want = {"NAND": 1 - (a & b), "XOR": a ^ b, "MUX": np.where(a == 1, b, bits[2] if nin == 3 else 0)}[args.op]
 
     fp64_peak = eng.measure_fp64_peak()
 
@@ -298,19 +437,10 @@ def main():
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    st = eng.stats()
-    launches = int(st.launches)
-    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    launches = int(eng.stats().launches)
+    ms_step = _max_over_ranks(torch, dist, dev, e0.elapsed_time(e1)) / args.steps
     value = world * pbs_per_step / (ms_step * 1e-3)
-    verified = None
-    if rank == 0:
-        a, b = bits[0], bits[1]
-        want = {"NAND": 1 - (a & b), "XOR": a ^ b, "MUX": np.where(a == 1, b, bits[2] if nin == 3 else 0)}[args.op]
-        verified = bool(np.array_equal(ks.decrypt(eng.download(base + nin * B, B)), want))
+    ok = bool(np.array_equal(ks.decrypt(eng.download(base + nin * B, B)), want))
 
     # ---- end to end through the host-buffer C-ABI call (upload + run + download inside the timed region)
     e2e_steps = max(1, min(args.steps, 3))
@@ -322,28 +452,22 @@ def main():
         eng.gate_batch_host(args.op, pinned_in[0].numpy(), pinned_in[1].numpy(), cc, out=pinned_out.numpy())
     e1.record(stream)
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps
+    e2e_ms = _max_over_ranks(torch, dist, dev, e0.elapsed_time(e1)) / e2e_steps
     e2e_value = world * pbs_per_step / (e2e_ms * 1e-3)
-    if rank == 0:
-        verified = verified and bool(np.array_equal(ks.decrypt(pinned_out.numpy()), want))
+    ok = ok and bool(np.array_equal(ks.decrypt(pinned_out.numpy()), want))
+    verified = _all_true(torch, dist, dev, ok)          # every rank's decrypted outputs, device-resident and e2e
 
     # ---- the other two gate types configs[1] names, same batch, device-resident (2 warm-up + 2 timed launches each)
     other = {}
     if not args.no_other_ops:
-        eng.enable_timing(True)
         for op in ("NAND", "XOR", "MUX"):
             if op == args.op:
                 continue
             n_in = 3 if op == "MUX" else 2
             eng.reserve(base + (n_in + 1) * B)
+            third = rng.integers(0, 2, size=B)
             if n_in > nin:                              # MUX needs a third operand block: device-side encryption
-                if rank == 0:
-                    eng.encrypt_bits(ks.lwe_key, rng.integers(0, 2, size=B), base + 2 * B, seed=78)
-                else:
-                    eng.upload(base + 2 * B, rng.integers(-2**31, 2**31, size=(B, words), dtype=np.int64).astype(np.int32))
+                eng.encrypt_bits(ks.lwe_key, third, base + 2 * B, seed=78 + rank)
             g2 = make_gates(op, idx, B + idx, n_in * B + idx, in2=(2 * B + idx) if op == "MUX" else None)
             for _ in range(2):
                 eng.gates(g2)
@@ -354,27 +478,35 @@ def main():
                 eng.gates(g2)
             e1.record(stream)
             barrier()
-            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
-            if dist is not None:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_op = float(t.item()) / 2
+            ms_op = _max_over_ranks(torch, dist, dev, e0.elapsed_time(e1)) / 2
             per = 2 if op == "MUX" else 1
-            other[op] = {"gpu_launches": int(eng.stats().launches), "pbs_per_s": world * B * per / (ms_op * 1e-3), "gates_per_s": world * B / (ms_op * 1e-3),
-                         "ms_per_step": ms_op, "pbs_per_gate": per}
-        eng.enable_timing(False)
+            c3 = third if n_in > nin else (bits[2] if nin == 3 else None)
+            w2 = {"NAND": 1 - (a & b), "XOR": a ^ b, "MUX": np.where(a == 1, b, c3) if c3 is not None else None}[op]
+            ok2 = bool(np.array_equal(ks.decrypt(eng.download(base + n_in * B, B)), w2))
+            other[op] = {"gpu_launches": int(eng.stats().launches), "pbs_per_s": world * B * per / (ms_op * 1e-3),
+                         "gates_per_s": world * B / (ms_op * 1e-3), "ms_per_step": ms_op, "pbs_per_gate": per,
+                         "verified": _all_true(torch, dist, dev, ok2)}
 
-    # ---- encrypted face matches/s on a bounded number of templates per GPU
-    face = face_opt = face_m2 = None
-    if not args.no_face_match and args.face_templates > 0:
-        face = face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=0)
-        face_m2 = face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=2)
-        face_opt = face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=3)
+    # ---- the other BASELINE configs as legs
+    face_strong = face_opt = face_m2 = circuits = None
+    if not args.no_face_match:
+        if args.face_total > 0:
+            face_strong = face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=0, total=args.face_total)
+        if args.face_templates > 0:
+            face_m2 = face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=2)
+            face_opt = face_match_leg(args, ks, eng, dist, rank, world, local, torch, np, mode=3)
+    if args.circuit_instances > 0:
+        circuits = circuits_leg(args, ks, eng, dist, rank, world, local, torch, np)
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    if verified is False or any(f and f.get("verified") is False for f in (face, face_m2, face_opt)):
+    bad = [verified is False] + [f is not None and f.get("verified") is False for f in (face_strong, face_m2, face_opt)]
+    bad += [v.get("verified") is False for v in other.values()]
+    if circuits:
+        bad += [isinstance(v, dict) and v.get("verified") is False for v in circuits.values()]
+    if any(bad):
         print("ERROR: decrypted outputs of the timed work are wrong", file=sys.stderr)
         sys.exit(1)
 
@@ -395,16 +527,12 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved_tf = pbs_per_step * F_PBS / (br_ms * 1e-3) / 1e12
     ks_bytes = KSK_BYTES + B * (4100 + 2524)
+    cfg = workload_config(args)
     line = {
         "metric": "bootstrapped gates/s (PBS/s)", "value": value, "unit": "PBS/s", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"gate-bootstrap microbench (BASELINE configs[1]): batch of {B} boots{args.op} per GPU on "
-                               "random ciphertexts, n=630 N=1024 k=1 l=3 Bgbit=7, keyswitch t=8 base 4",
-                   "batch_per_gpu": B, "op": args.op, "keys": key_note,
-                   "l2": "working set per step (inputs, extracted samples, outputs, keys) is 315 MB > 126 MB L2; "
-                         "no explicit flush",
-                   "decrypted_outputs_verified": verified},
+        "config": cfg, "keys": key_note, "decrypted_outputs_verified_on_every_rank": verified,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "PBS/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(nin * B * words * 4), "d2h_bytes_per_step": int(B * words * 4)},
@@ -412,21 +540,28 @@ def main():
         "kernel_ms": {"blind_rotate": br_ms, "keyswitch": ks_ms},
         "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp64_peak, "traffic": NCU_TRAFFIC.get(B, {}).get("blind_rotate"),
+                     "kernel": "pbs_kernel_tm (blind rotation)", "kernel_ms": br_ms,
+                     "peak_source": "DFMA probe run live on this GPU by this process (peba1_cuda_measure_fp64_peak: 8 independent "
+                                    "DFMA chains per thread on every SM); MEASURED_PEAKS.json and the profiling guide have no "
+                                    "FP64 entry; scripts/ubench/fp64_rates.cu is the stand-alone probe (profiles/r2_fp64_rates.log)",
+                     "peak_nominal": FP64_PEAK_NOMINAL, "frac_nominal": achieved_tf / FP64_PEAK_NOMINAL,
+                     "traffic_source": NCU_SOURCE["blind_rotate"],
                      "note": "dominant kernel = blind rotation (FP64 vector pipe; neither hbm nor tensor applies). "
-                             "achieved = 162,570,240 flop/PBS x PBS per launch / CUDA-event time of the launch; peak = "
-                             "DFMA probe measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); traffic = "
-                             "DRAM bytes per launch from profiles/r1zz_pbs_kernel_tm_final_ncu.txt (the key stays L2-resident; "
-                             "captured on the one-exchange-buffer instantiation of the same kernel, which reads and "
-                             "writes the same global data)"},
-        "roofline_keyswitch": {"bound": "hbm", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                               "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak,
-                               "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"),
-                               "note": "algorithmic bytes = 62.0 MB key + batch x (4100 in + 2524 out); peak = "
-                                       "MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)")},
+                             "achieved = 162,570,240 flop/PBS x PBS per launch / CUDA-event time of the launch; traffic = "
+                             "DRAM bytes per launch (the key stays L2-resident)"},
+        "roofline_keyswitch": {"bound": "l2 (not hbm)", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                               "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": ks_ms,
+                               "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"), "traffic_source": NCU_SOURCE["keyswitch"],
+                               "note": "algorithmic bytes = 62.0 MB key + batch x (4100 in + 2524 out) against MEASURED_PEAKS.json "
+                                       "hbm_gbs" + ("" if peaks else " (fallback 6650)") + ": the HBM fraction is tiny by "
+                                       "construction — every ciphertext selects its own ~6,144 of the 24,576 key rows, so the key is "
+                                       "re-read from L2 per ciphertext tile; the kernel's own bound is the L2/L1 path (DESIGN.md §5 K2)"},
         "other_ops": other or None,
-        "face_match": face,
+        "face_match_strong": face_strong,
+        "face_match": ({k: v for k, v in face_strong.items() if k != "level_histogram_rank0"} if face_strong else None),
         "face_match_optimised": face_opt,
         "face_match_mode2": face_m2,
+        "circuits": circuits,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

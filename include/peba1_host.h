@@ -108,6 +108,13 @@ void peba1_encrypt_array_device(LweSample* array, int32_t nbelems, const int32_t
 /* The same for a list of arrays (arrays[k][i] <- bits[k * nbelems + i]) in ONE launch: a wave of templates. */
 void peba1_encrypt_array_list_device(LweSample* const* arrays, int32_t narrays, int32_t nbelems, const int32_t* bits,
                                      const TFheGateBootstrappingSecretKeySet* key, uint64_t seed);
+/* arrays[k][i] <- sample (k*nbelems + i) of a dense DEVICE buffer of (n+1)-word samples (e.g. the receive buffer of an
+   NCCL broadcast / scatter): one device-side scatter into the ciphertext pool, no bounce through host memory. */
+void peba1_sample_set_list_device(LweSample* const* arrays, int32_t narrays, int32_t nbelems, const void* device_words,
+                                  const TFheGateBootstrappingCloudKeySet* bk);
+/* Pool row of a sample whose value lives on the device (flushes pending work first); -1 for host values, constants and
+   negated aliases.  With peba1_cuda_pool_info this lets a caller hand result ciphertexts to a collective in place. */
+int64_t peba1_sample_device_slot(const LweSample* sample, const TFheGateBootstrappingCloudKeySet* bk);
 void peba1_decrypt_words(const TFheGateBootstrappingSecretKeySet* key, const int32_t* words, int64_t count, int32_t* bits);
 /* The libpeba1_cuda context behind a cloud key (created on first use); NULL without a device. */
 void* peba1_cuda_context_of(const TFheGateBootstrappingCloudKeySet* bk);

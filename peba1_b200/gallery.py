@@ -81,6 +81,43 @@ def distribute(dist, rank: int, world: int, device, torch, words: int, slots: in
     return probe_t.cpu().numpy(), bound_t.cpu().numpy(), mine_t.cpu().numpy()
 
 
+def distribute_device(dist, rank: int, world: int, device, torch, words: int, slots: int, bits: int, per_rank: int,
+                      client=None):
+    """As distribute, but what the collectives deliver STAYS on the device: returns torch int32 tensors
+    (probe [slots*bits, words], bound [24, words], templates [per_rank, slots*bits, words]) for device_vectors()."""
+    probe_t = torch.empty((slots * bits, words), dtype=torch.int32, device=device)
+    bound_t = torch.empty((24, words), dtype=torch.int32, device=device)
+    mine_t = torch.empty((per_rank, slots * bits, words), dtype=torch.int32, device=device)
+    chunks = None
+    if rank == 0:
+        pw, bw, gw = client
+        probe_t.copy_(torch.from_numpy(np.ascontiguousarray(pw)))
+        bound_t.copy_(torch.from_numpy(np.ascontiguousarray(bw)))
+        gw = np.ascontiguousarray(gw).reshape(world, per_rank, slots * bits, words)
+        chunks = [torch.from_numpy(gw[r]).to(device) for r in range(world)]
+    if dist is not None and world > 1:
+        dist.broadcast(probe_t, 0)
+        dist.broadcast(bound_t, 0)
+        dist.scatter(mine_t, chunks, src=0)
+    else:
+        mine_t.copy_(chunks[0])
+    torch.cuda.synchronize()
+    return probe_t, bound_t, mine_t
+
+
+def device_vectors(ks, tensor, count: int, slots: int, bits: int):
+    """`count` vectors of `slots` ciphertext arrays of `bits` samples bound to the rows of a device tensor
+    [count * slots * bits, words] by ONE device-side scatter into the ciphertext pool (peba1_sample_set_list_device)."""
+    LSP = C.POINTER(H.LweSample)
+    flat, out = [], []
+    for _ in range(count):
+        arrs = [ks.new_array(bits) for _ in range(slots)]
+        flat.extend(arrs)
+        out.append((arrs, (LSP * slots)(*arrs)))
+    ks.set_list_device(flat, bits, tensor.data_ptr())
+    return out
+
+
 def _host_vector(ks, w, slots: int, bits: int):
     LSP = C.POINTER(H.LweSample)
     arrs = []

@@ -838,6 +838,37 @@ void peba1_encrypt_array_list_device(LweSample* const* arrays, int32_t narrays, 
     }
     g_stats.device_encryptions += (uint64_t)total;
 }
+// arrays[k][i] <- sample (k*nbelems + i) of a dense DEVICE buffer ((n+1) words each), e.g. what an NCCL broadcast or
+// scatter delivered: the samples become pool-resident wires by one device-side scatter, nothing crosses PCIe.
+void peba1_sample_set_list_device(LweSample* const* arrays, int32_t narrays, int32_t nbelems, const void* device_words,
+                                  const TFheGateBootstrappingCloudKeySet* bk) {
+    if (narrays <= 0 || nbelems <= 0) return;
+    if (!arrays || !device_words) die("peba1_sample_set_list_device: bad arguments");
+    Engine* e = engine_of(bk);
+    if (e->tb) die("peba1_sample_set_list_device needs the CUDA engine (a test backend holds no device memory)");
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const int64_t total = (int64_t)narrays * nbelems;
+    std::vector<int64_t> slots((size_t)total);
+    for (int32_t k = 0; k < narrays; ++k)
+        for (int32_t i = 0; i < nbelems; ++i) {
+            const int64_t id = new_wire(e, 0);  // the sample owns the only reference
+            slots[(size_t)k * nbelems + i] = g_wires[id].slot = alloc_slot(e);
+            sample_assign(&arrays[k][i], (Handle)id << 1);
+        }
+    ensure_capacity(e);
+    CUCHK(e, peba1_cuda_upload_slots_device(e->ctx, slots.data(), 0, total, (const int32_t*)device_words));
+    g_stats.uploads += (uint64_t)total;
+}
+// the device pool row of a sample that already lives there (-1 otherwise; flushes pending work first): lets a caller
+// gather result ciphertexts on the device, e.g. as the send buffer of an NCCL all-gather
+int64_t peba1_sample_device_slot(const LweSample* sample, const TFheGateBootstrappingCloudKeySet* bk) {
+    Engine* e = engine_of(bk);
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    const Handle h = sample->peba1_handle;
+    if (h == 0 || is_const(h) || (h & 1)) return -1;  // host value, constant, or a negated alias: no row of its own
+    if (g_wires[h >> 1].level > 0 || g_wires[h >> 1].slot < 0) flush(e);
+    return g_wires[h >> 1].slot;
+}
 void peba1_encrypt_array_device(LweSample* array, int32_t nbelems, const int32_t* bits,
                                 const TFheGateBootstrappingSecretKeySet* key, uint64_t seed) {
     peba1_encrypt_array_list_device(&array, 1, nbelems, bits, key, seed);

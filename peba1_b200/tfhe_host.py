@@ -123,6 +123,9 @@ def load_library():
     L.import_gate_bootstrapping_ciphertext_fromFile.argtypes = [FP, LS, PS]
     L.delete_gate_bootstrapping_cloud_keyset.argtypes = [CK]
     L.peba1_sample_get_words.argtypes = [LS, i32p]
+    L.peba1_sample_set_list_device.argtypes = [C.POINTER(LS), C.c_int32, C.c_int32, C.c_void_p, CK]
+    L.peba1_sample_device_slot.restype = C.c_int64
+    L.peba1_sample_device_slot.argtypes = [LS, CK]
     L.peba1_new_cloud_keyset_from_arrays.restype = CK
     L.peba1_new_cloud_keyset_from_arrays.argtypes = [PS, i32p, i32p]
     L.peba1_cuda_context_of.restype = C.c_void_p
@@ -219,6 +222,11 @@ class KeySet:
         assert bits.size == len(arrs) * nbelems
         ptrs = (C.POINTER(LweSample) * len(arrs))(*arrs)
         self.L.peba1_encrypt_array_list_device(ptrs, len(arrs), nbelems, _i32(bits), self.sk, seed)
+
+    def set_list_device(self, arrs, nbelems: int, device_ptr: int):
+        """arrs[k][i] <- sample k*nbelems+i of a dense DEVICE buffer (one scatter on the GPU, no host bounce)."""
+        ptrs = (C.POINTER(LweSample) * len(arrs))(*arrs)
+        self.L.peba1_sample_set_list_device(ptrs, len(arrs), nbelems, C.c_void_p(device_ptr), self.cloud)
 
     def get_words(self, arr, count: int) -> np.ndarray:
         out = np.empty((count, self.words), dtype=np.int32)
