@@ -908,6 +908,125 @@ __global__ void __launch_bounds__(kKsThreads)
         if (w0 + q <= n) atomicAdd(out + w0 + q, r[q]);
 }
 
+// K2 for wide levels, TILED: the key is streamed once per TILE of ciphertexts instead of once per ciphertext.
+// The one-CTA-per-ciphertext kernel above pulls ~6,144 rows of 2.5 KB per ciphertext through the L1 data pipe: 214 GB of
+// L2->SM traffic per 16,384 ciphertexts (ncu r1s: lts 83 %, L1 70 % busy) for 62 MB of key.  Here a thread keeps 8 output
+// words of G ciphertexts in registers (8 G accumulators), loads the 3 rows of a digit position ONCE (its 8 words of each:
+// 6 LDG.128) and subtracts, per ciphertext, the row its digit selects.  The digit of a (position, ciphertext) is the
+// same for every thread of the group, so the selection is a warp-uniform branch around 8 integer subtractions; the key
+// traffic through L1/L2 drops G-fold.  A CTA = 2 groups of 80 threads (words 8tt .. 8tt+7 of a 640-word padded row),
+// i.e. 2 G ciphertexts; the digits of a chunk of coefficients wait in shared memory.  PARTS > 1 splits the 1,024
+// coefficients of a tile over several CTAs (finer load balance; partial sums by red.global.add after ks_init_kernel).
+// Integer additions mod 2^32 commute: the same words as the other two kernels (tests/test_gpu_parity.py).
+constexpr int kKsTileGroup = 80;            // threads per ciphertext group: 80 x 8 words = one padded key row
+constexpr int kKsTileThreads = 2 * kKsTileGroup;
+constexpr int kKsTileChunk = 64;            // coefficients per shared-memory chunk of digits
+
+template <int T, int BASEBIT, int G>
+__global__ void __launch_bounds__(kKsTileThreads)
+    keyswitch_tile_kernel(const int32_t* __restrict__ ksk, int n, int64_t kstride, int64_t stride,
+                          const int32_t* __restrict__ u, const KsJob* __restrict__ jobs, int64_t count, int parts,
+                          int32_t* __restrict__ pool) {
+    constexpr int BASE = 1 << BASEBIT;
+    constexpr uint32_t PREC_OFFSET = 1u << (32 - (1 + BASEBIT * T));
+    __shared__ __align__(16) uint32_t abar[kKsTileChunk][2 * G];
+    const int t = threadIdx.x, h = t / kKsTileGroup, tt = t % kKsTileGroup;
+    const int64_t tile = blockIdx.x / parts;
+    const int part = blockIdx.x % parts, span = kN / parts, i0 = part * span;
+    const int64_t g0 = tile * (2 * G);
+    uint4 acc[G][2];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g][0] = acc[g][1] = make_uint4(0, 0, 0, 0);
+    const uint32_t row_bytes = (uint32_t)kstride * 4u;
+    // words 4tt..4tt+3 and 320+4tt..320+4tt+3 of a 640-word row: both 16-byte loads of a warp are contiguous
+    const unsigned char* kp = reinterpret_cast<const unsigned char*>(ksk) + 16u * (uint32_t)tt;
+    for (int c0 = 0; c0 < span; c0 += kKsTileChunk) {
+        __syncthreads();  // the previous chunk's digits are no longer read
+        for (int g = 0; g < 2 * G; ++g) {
+            if (t < kKsTileChunk) {
+                uint32_t v = 0;  // a ciphertext beyond the batch: all digits 0
+                if (g0 + g < count) {
+                    const KsJob job = jobs[g0 + g];
+                    v = (uint32_t)u[(int64_t)job.u0 * kUStride + i0 + c0 + t] + PREC_OFFSET;
+                    if (job.u1 >= 0) v += (uint32_t)u[(int64_t)job.u1 * kUStride + i0 + c0 + t];
+                }
+                abar[t][g] = v;
+            }
+        }
+        __syncthreads();
+        // positions (i, j) of the chunk in one rolled loop (an unrolled body of 8 x G branches overflows the instruction
+        // cache: 37 ms instead of 11); the rows of position p + 1 are requested before position p is consumed
+        const unsigned char* kr = kp + (size_t)(i0 + c0) * (T * (BASE - 1)) * row_bytes;
+        uint4 r[3][2], nx[3][2];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            nx[d][0] = __ldg(reinterpret_cast<const uint4*>(kr + (size_t)d * row_bytes));
+            nx[d][1] = __ldg(reinterpret_cast<const uint4*>(kr + (size_t)d * row_bytes + 1280));
+        }
+        uint32_t a[G];
+#pragma unroll 1
+        for (int p = 0; p < kKsTileChunk * T; ++p) {
+            const int j = p & (T - 1);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { r[d][0] = nx[d][0]; r[d][1] = nx[d][1]; }
+            kr += (size_t)(BASE - 1) * row_bytes;
+            if (p + 1 < kKsTileChunk * T) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    nx[d][0] = __ldg(reinterpret_cast<const uint4*>(kr + (size_t)d * row_bytes));
+                    nx[d][1] = __ldg(reinterpret_cast<const uint4*>(kr + (size_t)d * row_bytes + 1280));
+                }
+            }
+            if (j == 0) {
+#pragma unroll
+                for (int q = 0; q < G / 4; ++q) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(&abar[p / T][h * G + 4 * q]);
+                    a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+                }
+            }
+            const int sh = 32 - (j + 1) * BASEBIT;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint32_t d = (a[g] >> sh) & (BASE - 1);
+                if (d == 1) {
+                    acc[g][0].x -= r[0][0].x; acc[g][0].y -= r[0][0].y; acc[g][0].z -= r[0][0].z; acc[g][0].w -= r[0][0].w;
+                    acc[g][1].x -= r[0][1].x; acc[g][1].y -= r[0][1].y; acc[g][1].z -= r[0][1].z; acc[g][1].w -= r[0][1].w;
+                } else if (d == 2) {
+                    acc[g][0].x -= r[1][0].x; acc[g][0].y -= r[1][0].y; acc[g][0].z -= r[1][0].z; acc[g][0].w -= r[1][0].w;
+                    acc[g][1].x -= r[1][1].x; acc[g][1].y -= r[1][1].y; acc[g][1].z -= r[1][1].z; acc[g][1].w -= r[1][1].w;
+                } else if (d == 3) {
+                    acc[g][0].x -= r[2][0].x; acc[g][0].y -= r[2][0].y; acc[g][0].z -= r[2][0].z; acc[g][0].w -= r[2][0].w;
+                    acc[g][1].x -= r[2][1].x; acc[g][1].y -= r[2][1].y; acc[g][1].z -= r[2][1].z; acc[g][1].w -= r[2][1].w;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int64_t gi = g0 + h * G + g;
+        if (gi >= count) break;
+        const KsJob job = jobs[gi];
+        uint32_t r[8] = {acc[g][0].x, acc[g][0].y, acc[g][0].z, acc[g][0].w, acc[g][1].x, acc[g][1].y, acc[g][1].z, acc[g][1].w};
+        int32_t* out = pool + job.out_slot * stride;
+        if (parts == 1) {
+            uint32_t bsum = (uint32_t)u[(int64_t)job.u0 * kUStride + kN] + (uint32_t)job.c0;  // b' (+ b'' + c0) goes to word n
+            if (job.u1 >= 0) bsum += (uint32_t)u[(int64_t)job.u1 * kUStride + kN];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int w = (q < 4 ? 4 * tt : 320 + 4 * tt) + (q & 3);
+                if (w == n) r[q] += bsum;
+                if (w <= n) out[w] = (int32_t)r[q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int w = (q < 4 ? 4 * tt : 320 + 4 * tt) + (q & 3);
+                if (w <= n) atomicAdd(reinterpret_cast<unsigned int*>(out) + w, r[q]);
+            }
+        }
+    }
+}
+
 // K4.  out = sign*in + (0, cst); in < 0: absent.
 __global__ void linear_kernel(int32_t* __restrict__ pool, int64_t stride, int n, const int64_t* __restrict__ in,
                               const int32_t* __restrict__ sign, const int32_t* __restrict__ cst,
@@ -1028,6 +1147,9 @@ struct peba1_cuda_ctx {
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
     int narrow_two_buffers = 0;  // 1: the narrow shapes (fixed grids of 1..8 teams) run on TeamSmemTm2 as well (not measured yet)
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
+    int ks_tile = 0;         // ciphertexts per group of the tiled keyswitch (8, 12, 16; 0 = off), 2 groups per CTA
+    int ks_tile_parts = 1;   // CTAs per tile (coefficient ranges, partial sums by red.global.add)
+    int64_t ks_tile_min = 4096;  // levels narrower than this keep the per-ciphertext kernels
     int64_t ks_split = -1;   // CTAs per ciphertext in the keyswitch of a narrow level: -1 by batch size, 0 never, else fixed (power of 2)
     int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..10 are the
                              // measured alternatives
@@ -1342,6 +1464,23 @@ int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t co
         CU(cudaGetLastError());
         if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
         c->stats.launches += 2;
+        c->stats.keyswitches += (uint64_t)count;
+        return 0;
+    }
+    // wide level: the tiled kernel (key streamed once per tile of ciphertexts)
+    if (c->ks_tile > 0 && count >= (int64_t)c->ks_tile_min) {
+        const int parts = c->ks_tile_parts;
+        const int64_t per_cta = 2 * c->ks_tile;
+        const unsigned tgrid = (unsigned)(((count + per_cta - 1) / per_cta) * parts);
+        if (parts > 1) ks_init_kernel<<<(unsigned)count, 160, 0, c->stream>>>(c->p.n, c->pool_stride, u, jobs, count, pool);
+        switch (c->ks_tile) {
+            case 8: keyswitch_tile_kernel<8, 2, 8><<<tgrid, kKsTileThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, parts, pool); break;
+            case 12: keyswitch_tile_kernel<8, 2, 12><<<tgrid, kKsTileThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, parts, pool); break;
+            default: keyswitch_tile_kernel<8, 2, 16><<<tgrid, kKsTileThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, parts, pool); break;
+        }
+        CU(cudaGetLastError());
+        if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
+        c->stats.launches += parts > 1 ? 2 : 1;
         c->stats.keyswitches += (uint64_t)count;
         return 0;
     }
@@ -2088,6 +2227,20 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         if (value == 0) value = 1;
         if (value != 1 && value != 2 && value != 4 && value != 6 && value != 8) return fail(PEBA1_EINVAL, "ks_group must be 1, 2, 4, 6 or 8");
         c->ks_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_tile")) {
+        if (value != 0 && value != 8 && value != 12 && value != 16) return fail(PEBA1_EINVAL, "ks_tile must be 0, 8, 12 or 16");
+        c->ks_tile = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_tile_parts")) {
+        if (value < 1 || value > 16 || (value & (value - 1))) return fail(PEBA1_EINVAL, "ks_tile_parts must be 1, 2, 4, 8 or 16");
+        c->ks_tile_parts = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_tile_min")) {
+        c->ks_tile_min = value;
         return 0;
     }
     if (!strcmp(name, "ks_split")) {

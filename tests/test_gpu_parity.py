@@ -188,10 +188,20 @@ def test_kernel_variants_agree(engine, keys):
         for grp in (2, 4, 6, 8):
             engine.set_option("ks_group", grp)
             assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), grp
+        engine.set_option("ks_group", 1)
+        engine.set_option("ks_tile_min", 1)      # the tiled keyswitch (key streamed once per tile of ciphertexts), also split
+        for tile, parts in ((8, 1), (12, 1), (16, 1), (8, 4), (16, 2)):
+            engine.set_option("ks_tile", tile)
+            engine.set_option("ks_tile_parts", parts)
+            assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), (tile, parts)
+        engine.set_option("ks_tile", 0)
     finally:
         engine.set_option("kernel_variant", 1)
         engine.set_option("tm_teams", 0)
         engine.set_option("ks_group", 1)
+        engine.set_option("ks_tile", 0)
+        engine.set_option("ks_tile_parts", 1)
+        engine.set_option("ks_tile_min", 4096)
         engine.set_option("pair_min_batch", -1)
 
 
