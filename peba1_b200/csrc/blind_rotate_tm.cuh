@@ -90,25 +90,45 @@ struct __align__(16) TeamSmemTm2S : TeamSmemTm2 {
     static constexpr bool kShfl = true;
 };
 
-// The CROSS-TEAM exchange of every transform through TENSOR MEMORY instead of shared memory (kXTm): a thread stores its 8
-// complex values with tcgen05.st.32x32b and the team reads them back with tcgen05.ld.16x256b, whose fragment layout
-// transposes two lane bits against the index of the 64-bit unit inside a 256-bit group (probed:
-// scripts/ubench/tmem_xchg_probe.cu) — none of it touches the LSU / L1 data pipe, which is this kernel's busiest.  The
-// inner exchange stays in shared memory (one warp-local 8 KB buffer).  Tensor-memory columns: [0,256) sums, [256,320)
-// twiddles, [320,384) decomposition input, [384,512) exchange (32 per warp group); the thread-own accumulator copies go
-// back to shared memory.
+// The CROSS-TEAM exchange of every transform through TENSOR MEMORY instead of shared memory (kXTm; kernel_variant 11).
+// The shared-memory / L1 data pipe is this kernel's busiest unit, and the cross-team exchange is a third of its traffic
+// (8 STS.128 + 8 LDS.128 per thread and transform).  Tensor memory is a separate datapath: a thread stores its 8 complex
+// values with tcgen05.st.32x32b (row = lane, 32 columns) and reads with tcgen05.ld.16x256b, whose fragment layout hands
+// thread t the 64-bit units (t & 3) of lanes (t >> 2) and (t >> 2) + 8 — a transposition between two lane bits and the
+// unit index that never touches the LSU (layout probed on the device: scripts/ubench/tmem_xchg_probe.cu).
+//
+// For that, the two warps of a team must share a tensor-memory lane quarter (warp % 4): a team is warps (w, w + 4), thread
+// tid = 32 wb + lane.  Exchange 1 moves register index k0 <-> thread bits (wb, L4, L3) = b:
+//     store   thread (wb, lane), value k0  ->  own block, column 16 (k0 >> 2) + 8 isIm + 2 (k0 & 3) + word
+//     load    warp wb' reads columns [16 wb', +16) of BOTH blocks (S = 0, 1), lane halves H = 0, 1: thread t receives
+//             b = 4 S + 2 H + b0 of  m = 8 b + (t >> 2),  k0 = 4 wb' + (t & 3)
+// so AFTER the exchange physical thread (wb', t) is the logical thread hi = k0 = 4 wb' + (t & 3), lo = c = t >> 2 of the
+// radix-8 network for the SECOND pass only: the inner exchange, which stays in shared memory and is warp-local, is written
+// in that permuted position and read back by the plain thread (tid >> 3, tid & 7), so transform outputs, key columns and
+// sums sit where they sit in every other layout (a permuted position there would un-coalesce the key loads: 8
+// consecutive lanes would touch 4 different 128-byte lines).  Its swizzle gains the term 2 (h & 3): a 16-byte access is
+// served 8 lanes at a time and 8 consecutive lanes of the permuted side hold 4 different h.  The inverse transform runs
+// both trips backwards (tcgen05.st.16x256b into both blocks, tcgen05.ld.32x32b of the own block).
+// Tensor-memory columns: [0,256) sums, [256,320) tw1 of wb = 0 / 1, [320,352) tw2, [352,480) exchange (32 per warp).
+// The decomposition input and the thread-own accumulator words live in shared memory again (no columns left).
 struct __align__(16) TeamSmemTmX {
     static constexpr bool kAliased = true, kDouble = false, kShfl = false, kClear = true, kXTm = true;
-    static constexpr int kTw1 = kTmTw1, kTw2 = kTmTw2, kZero = kTmZero;
-    static constexpr int kTv = 320, kOwn = -1, kX = 384;
-    double2  ex[kM];
+    static constexpr int kTw1 = kTmTw1, kTw2 = 320, kZero = -1;
+    static constexpr int kTv = -1, kOwn = -1, kX = 352;
+    double2  ex[kM];          // inner exchange only (warp-local regions)
     int32_t  acc[2][kN];
+    uint4    tv[4][kTeam];    // decomposition input between the digit levels: tv[q][tid] = words 4q..4q+3 of thread tid
     uint16_t bara[640];
     unsigned long long ex1_free;  // unused
     unsigned long long pad_;
     PEBA1_HD double2* e1(int) { return ex; }
     PEBA1_HD double2* e2(int) { return ex; }
 };
+// word index of value k0 (component part = 0 re.lo, 1 re.hi, 2 im.lo, 3 im.hi) in the 32-column block a thread stores
+// before / loads after the 32x32b side of the trip
+PEBA1_HD constexpr int xtm_col(int k0, int part) { return 16 * (k0 >> 2) + 8 * (part >> 1) + 2 * (k0 & 3) + (part & 1); }
+// register index of value b on the 16x256b side: four accesses q = b >> 1 (block S = q >> 1, lane half H = q & 1) of 8 words
+PEBA1_HD constexpr int xtm_reg(int b, int part) { return 8 * (b >> 1) + 4 * (part >> 1) + 2 * (b & 1) + (part & 1); }
 
 // In-place transposition x[j] of lane l  <->  x[l] of lane j over the 8 lanes that share tid >> 3 (lo = tid & 7).
 template <class Env>
@@ -175,7 +195,8 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
     double2* const ex1 = sm.e1(par);
     double2* const ex2 = sm.e2(par);
     uint32_t w[32];
-    env.tmem_ld32(SM::kTw1, w);  // in flight while the first pass computes
+    if constexpr (SM::kXTm) env.tmem_ld32(env.tw1_col(), w);
+    else env.tmem_ld32(SM::kTw1, w);  // in flight while the first pass computes
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul(x[a], w32(a));
     radix8<false>(x);
@@ -185,22 +206,39 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
         uint32_t v[32];
 #pragma unroll
         for (int k0 = 0; k0 < 8; ++k0)
-            c_to_words(cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3])), v[4 * k0], v[4 * k0 + 1],
-                       v[4 * k0 + 2], v[4 * k0 + 3]);
-        env.xtm_exchange(v);
+            c_to_words(cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3])), v[xtm_col(k0, 0)],
+                       v[xtm_col(k0, 1)], v[xtm_col(k0, 2)], v[xtm_col(k0, 3)]);
+        env.xtm_exchange_fwd(v);
         env.tmem_ld32(SM::kTw2, w);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) x[b] = words_to_c(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
+        for (int b = 0; b < 8; ++b) x[b] = words_to_c(v[xtm_reg(b, 0)], v[xtm_reg(b, 1)], v[xtm_reg(b, 2)], v[xtm_reg(b, 3)]);
+        radix8<false>(x);
+        env.tmem_wait_ld();
+        // Inner exchange.  This thread is logical (hp, lp) of the network now (see TeamSmemTmX); the READER side is the
+        // plain thread (hi, lo) = (tid >> 3, tid & 7) again, so everything after the transform — key columns, sums, the
+        // inverse — sees the same positions as in the other layouts.  Writers and readers of a region [64 h, +64) are
+        // lanes of one warp.  cell(h, k1, c) = 64 h + 8 k1 + (c ^ k1 ^ 2 (h & 3)) is conflict-free for both lane patterns.
+        const int hp = env.xhi(), lp = env.xlo(), sp = 2 * (hp & 3), ss = 2 * (hi & 3);
+        env.warp_sync();  // the region's readers of the previous transform are done
+        ex2[64 * hp + (lp ^ sp)] = x[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1)
+            ex2[64 * hp + 8 * k1 + (lp ^ k1 ^ sp)] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
+        env.warp_sync();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = ex2[64 * hi + 8 * lo + (c ^ lo ^ ss)];
+        radix8<false>(x);
+        return;
     } else {
-    if (!SM::kDouble) env.ex1_acquire();  // every reader of the previous transform's ex1 is done (split-phase)
+        if (!SM::kDouble) env.ex1_acquire();  // every reader of the previous transform's ex1 is done (split-phase)
 #pragma unroll
-    for (int k0 = 0; k0 < 8; ++k0)
-        ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
-    env.tmem_ld32(SM::kTw2, w);  // in flight across the barrier, the loads and the second pass
-    env.team_sync();
+        for (int k0 = 0; k0 < 8; ++k0)
+            ex1[64 * k0 + tid] = cmul(x[k0], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
+        env.tmem_ld32(SM::kTw2, w);  // in flight across the barrier, the loads and the second pass
+        env.team_sync();
 #pragma unroll
-    for (int b = 0; b < 8; ++b) x[b] = ex1[64 * hi + 8 * b + lo];
-    if (!SM::kAliased && !SM::kDouble) env.ex1_release();
+        for (int b = 0; b < 8; ++b) x[b] = ex1[64 * hi + 8 * b + lo];
+        if (!SM::kAliased && !SM::kDouble) env.ex1_release();
     }
     radix8<false>(x);
     env.tmem_wait_ld();
@@ -208,19 +246,6 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
 #pragma unroll
     for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
 #else
-#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 4
-    if constexpr (SM::kXTm) {
-        uint32_t v[32];
-        c_to_words(x[0], v[0], v[1], v[2], v[3]);
-#pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1)
-            c_to_words(cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3])), v[4 * k1], v[4 * k1 + 1],
-                       v[4 * k1 + 2], v[4 * k1 + 3]);
-        env.xtm_inner(v);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = words_to_c(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-    } else
-#endif
     if (SM::kShfl) {
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
@@ -236,7 +261,7 @@ PEBA1_HD void team_fft_forward_tm(Env& env, double2 (&x)[8], SM& sm) {
         for (int c = 0; c < 8; ++c) x[c] = ex2[64 * hi + 8 * lo + (c ^ lo)];
     }
 #endif
-    if (SM::kAliased && !SM::kDouble && !SM::kXTm) env.ex1_release();
+    if (SM::kAliased && !SM::kDouble) env.ex1_release();
     radix8<false>(x);
 }
 
@@ -250,21 +275,34 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
     uint32_t w[32];
     env.tmem_ld32(SM::kTw2, w);
     radix8<true>(x);
-    env.tmem_wait_ld();
-#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 4
     if constexpr (SM::kXTm) {
+        // the forward transform's inner exchange backwards: written by the plain thread (hi, lo), read by logical (hp, lp);
+        // the twiddle of element (k1, c) is applied by the reader (it holds w64^(c k1) for c = lp): the same product
+        const int hp = env.xhi(), lp = env.xlo(), sp = 2 * (hp & 3), ss = 2 * (hi & 3);
+        env.warp_sync();  // the region's readers of the previous transform are done
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ex2[64 * hi + 8 * lo + (c ^ lo ^ ss)] = x[c];
+        env.warp_sync();
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) x[k1] = ex2[64 * hp + 8 * k1 + (lp ^ k1 ^ sp)];
+        env.tmem_wait_ld();
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) x[k1] = cmul_conj(x[k1], words_to_c(w[4 * k1], w[4 * k1 + 1], w[4 * k1 + 2], w[4 * k1 + 3]));
+        radix8<true>(x);
         uint32_t v[32];
-        c_to_words(x[0], v[0], v[1], v[2], v[3]);
 #pragma unroll
-        for (int c = 1; c < 8; ++c)
-            c_to_words(cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3])), v[4 * c], v[4 * c + 1],
-                       v[4 * c + 2], v[4 * c + 3]);
-        env.tmem_ld32(SM::kTw1, w);
-        env.xtm_inner(v);
+        for (int b = 0; b < 8; ++b) c_to_words(x[b], v[xtm_reg(b, 0)], v[xtm_reg(b, 1)], v[xtm_reg(b, 2)], v[xtm_reg(b, 3)]);
+        env.xtm_exchange_inv(v, w);  // also fetches tw1 into w (one tcgen05.wait::ld for both): w is not live across the trip
 #pragma unroll
-        for (int k1 = 0; k1 < 8; ++k1) x[k1] = words_to_c(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
-    } else
-#endif
+        for (int k0 = 0; k0 < 8; ++k0)
+            x[k0] = cmul_conj(words_to_c(v[xtm_col(k0, 0)], v[xtm_col(k0, 1)], v[xtm_col(k0, 2)], v[xtm_col(k0, 3)]),
+                              words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
+        radix8<true>(x);
+#pragma unroll
+        for (int a = 1; a < 8; ++a) x[a] = cmul_conj(x[a], w32(a));
+        return;
+    }
+    env.tmem_wait_ld();
     if (SM::kShfl) {
 #pragma unroll
         for (int c = 1; c < 8; ++c) x[c] = cmul_conj(x[c], words_to_c(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]));
@@ -272,7 +310,6 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
         lane8_transpose(env, x, lo);
     } else {
         if (SM::kDouble) {}                        // a fresh buffer: nobody reads it any more (see TeamSmemTm2)
-        else if (SM::kXTm) env.warp_sync();        // the buffer only carries the warp-local inner exchange
         else if (SM::kAliased) env.ex1_acquire();  // the previous transform's cross-team readers of this region are done
         else env.warp_sync();                      // previous readers of ex2 are done
         ex2[64 * hi + 8 * lo + lo] = x[0];
@@ -285,16 +322,6 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
         for (int k1 = 0; k1 < 8; ++k1) x[k1] = ex2[64 * hi + 8 * k1 + (lo ^ k1)];
     }
     radix8<true>(x);
-    if constexpr (SM::kXTm) {
-        uint32_t v[32];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) c_to_words(x[b], v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
-        env.xtm_exchange(v);  // its tcgen05.wait::ld also covers the twiddle load above
-#pragma unroll
-        for (int k0 = 0; k0 < 8; ++k0)
-            x[k0] = cmul_conj(words_to_c(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]),
-                              words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
-    } else {
     if (SM::kShfl) {}                     // kDouble layout, inner exchange not in memory: a fresh buffer
     else if (SM::kAliased) env.warp_sync();    // the region's readers above are done before it is rewritten
     else env.ex1_acquire();               // previous readers of ex1 are done
@@ -306,7 +333,6 @@ PEBA1_HD void team_fft_inverse_tm(Env& env, double2 (&x)[8], SM& sm) {
     for (int k0 = 0; k0 < 8; ++k0)
         x[k0] = cmul_conj(ex1[64 * k0 + tid], words_to_c(w[4 * k0], w[4 * k0 + 1], w[4 * k0 + 2], w[4 * k0 + 3]));
     if (!SM::kDouble) env.ex1_release();
-    }
     radix8<true>(x);
 #pragma unroll
     for (int a = 1; a < 8; ++a) x[a] = cmul_conj(x[a], w32(a));
@@ -406,11 +432,24 @@ PEBA1_HD void blind_rotate_team_tm(Env& env, SM& sm, const double2* __restrict__
                         tv[8 + a] = (uint32_t)rot_diff<Env>(sm.acc[poly], 64 * a + tid + 512, abar) + offset;
                     }
                 }
-                env.tmem_st16(env.tv_col, tv);
+                if constexpr (SM::kXTm) {  // no tensor-memory columns left: the thread's own 64 bytes of shared memory
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sm.tv[q][tid] = make_uint4(tv[4 * q], tv[4 * q + 1], tv[4 * q + 2], tv[4 * q + 3]);
+                } else {
+                    env.tmem_st16(env.tv_col, tv);
+                }
             } else {
-                env.tmem_wait_st();
-                env.tmem_ld16(env.tv_col, tv);
-                env.tmem_wait_ld();
+                if constexpr (SM::kXTm) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 t4 = sm.tv[q][tid];
+                        tv[4 * q] = t4.x; tv[4 * q + 1] = t4.y; tv[4 * q + 2] = t4.z; tv[4 * q + 3] = t4.w;
+                    }
+                } else {
+                    env.tmem_wait_st();
+                    env.tmem_ld16(env.tv_col, tv);
+                    env.tmem_wait_ld();
+                }
             }
 #else
             if (p == 0) {

@@ -142,21 +142,32 @@ struct DevEnvTm {
     int tv_col = 0;           // 16 tensor-memory columns where the decomposition input waits between digit levels
     int own_col = 0;          // 16 tensor-memory columns with this thread's own words of the body accumulator
     int xpar = 0;             // which exchange buffer the next transform uses (double-buffered layouts)
-    int x_col = 0;            // kXTm layouts: this warp's 32 exchange columns, and the team partner's
-    int x_peer = 0;
-    int x_half = 0;           // which 16 of a block's 32 columns this warp reads back
-    // Cross-team exchange through tensor memory (TeamSmemTmX): every thread stores its 32 words, the team meets, and each
-    // warp reads 16 columns of its own and of its partner's block in the transposing 16x256b shape.
-    __device__ __forceinline__ void xtm_exchange(uint32_t (&v)[32]) const {
-        team_sync();  // the partner has read what the previous transform left in my columns
-        tmem_st_x32(tm_base + (uint32_t)x_col, v);
+    // ---- kXTm layouts (TeamSmemTmX): the cross-team exchange through tensor memory
+    // (all derived from threadIdx on the spot: as fields they would sit in six registers for the whole kernel)
+    __device__ __forceinline__ int xgrp() const { return (int)(threadIdx.x >> 7); }         // warp / 4: the column block
+    __device__ __forceinline__ int xwb() const { return (int)(threadIdx.x >> 7) & 1; }      // tid = 32 wb + lane
+    __device__ __forceinline__ int x_col() const { return TeamSmemTmX::kX + 32 * xgrp(); }  // this warp's 32 exchange columns
+    __device__ __forceinline__ int x_peer() const { return TeamSmemTmX::kX + 32 * (xgrp() ^ 1); }  // the team partner's
+    __device__ __forceinline__ int tw1_col() const { return TeamSmemTmX::kTw1 + 32 * xwb(); }
+    // logical position after the exchange: hi = 4 wb + (lane & 3), lo = lane >> 2
+    __device__ __forceinline__ int xhi() const { return 4 * xwb() + (int)(threadIdx.x & 3); }
+    __device__ __forceinline__ int xlo() const { return (int)(threadIdx.x & 31) >> 2; }
+    // (Write-after-read protection of the blocks by a split-phase mbarrier instead of the first team barrier of a trip was
+    // measured: 155.7 ms instead of 147.6 — the polling costs more issue slots than the rendezvous, as with the "buffer
+    // free" mbarrier of TeamSmemTm.)
+    // forward: 32x32b store of the own block, 16x256b loads of columns [16 wb, +16) of both blocks (S = 0, 1: the block
+    // of the team's warp S) and both lane halves
+    __device__ __forceinline__ void xtm_exchange_fwd(uint32_t (&v)[32]) const {
+        team_sync();  // the partner has read what the previous trip left in the blocks
+        tmem_st_x32(tm_base + (uint32_t)x_col(), v);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         team_sync();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint32_t a = tm_base + (uint32_t)((q & 2 ? x_peer : x_col) + 16 * x_half) + ((uint32_t)(16 * (q & 1)) << 16);
+            const int S = q >> 1, H = q & 1;
+            const uint32_t a = tm_base + (uint32_t)((S == xwb() ? x_col() : x_peer()) + 16 * xwb()) + ((uint32_t)(16 * H) << 16);
             asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(v[8 * q]), "=r"(v[8 * q + 1]), "=r"(v[8 * q + 2]), "=r"(v[8 * q + 3]), "=r"(v[8 * q + 4]),
                            "=r"(v[8 * q + 5]), "=r"(v[8 * q + 6]), "=r"(v[8 * q + 7])
@@ -164,32 +175,26 @@ struct DevEnvTm {
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     }
-#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 4
-    // WHAT-IF: the inner exchange as one more tensor-memory trip (two lane bits) plus one shuffle stage (the third bit)
-    __device__ __forceinline__ void xtm_inner(uint32_t (&v)[32]) const {
-        team_sync();  // stands for: the partner is done with my columns
-        tmem_st_x32(tm_base + (uint32_t)x_col, v);
+    // inverse: the same trip backwards — 16x256b stores into both blocks, 32x32b load of the own block
+    __device__ __forceinline__ void xtm_exchange_inv(uint32_t (&v)[32], uint32_t (&tw)[32]) const {
+        team_sync();  // the partner is done with the blocks' previous contents
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int S = q >> 1, H = q & 1;
+            const uint32_t a = tm_base + (uint32_t)((S == xwb() ? x_col() : x_peer()) + 16 * xwb()) + ((uint32_t)(16 * H) << 16);
+            asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         ::"r"(a), "r"(v[8 * q]), "r"(v[8 * q + 1]), "r"(v[8 * q + 2]), "r"(v[8 * q + 3]), "r"(v[8 * q + 4]),
+                           "r"(v[8 * q + 5]), "r"(v[8 * q + 6]), "r"(v[8 * q + 7])
+                         : "memory");
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const uint32_t a = tm_base + (uint32_t)x_col + ((uint32_t)(16 * q) << 16);
-            asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(v[16 * q]), "=r"(v[16 * q + 1]), "=r"(v[16 * q + 2]), "=r"(v[16 * q + 3]), "=r"(v[16 * q + 4]),
-                           "=r"(v[16 * q + 5]), "=r"(v[16 * q + 6]), "=r"(v[16 * q + 7]), "=r"(v[16 * q + 8]), "=r"(v[16 * q + 9]),
-                           "=r"(v[16 * q + 10]), "=r"(v[16 * q + 11]), "=r"(v[16 * q + 12]), "=r"(v[16 * q + 13]),
-                           "=r"(v[16 * q + 14]), "=r"(v[16 * q + 15])
-                         : "r"(a));
-        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        team_sync();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_ld_x32(tm_base + (uint32_t)x_col(), v);
+        tmem_ld_x32(tm_base + (uint32_t)tw1_col(), tw);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const bool up = (threadIdx.x & 4) != 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {  // one butterfly stage: half of the 32 words change hands
-            const uint32_t out = up ? v[j] : v[16 + j];
-            const uint32_t in = __shfl_xor_sync(0xffffffffu, out, 4);
-            if (up) v[j] = in; else v[16 + j] = in;
-        }
     }
-#endif
     __device__ __forceinline__ int flip() { const int p = xpar; xpar ^= 1; return p; }
     // Split-phase write-after-read protection of the cross-team exchange buffer: a warp signals as soon as its reads
     // are done, the next writer waits just before writing, one whole transform pass later, so nobody actually blocks.
@@ -386,30 +391,51 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     __shared__ long long next_job[TEAMS];
     __shared__ uint32_t tm_alloc_base;
     const int warp = threadIdx.x >> 5;
-    const int team = threadIdx.x / kTeam;
+    // A team is two warps.  Ordinarily warps (2t, 2t + 1); with the tensor-memory exchange the two must share a lane quarter
+    // (warp % 4), so team t = (warp & 3) + 4 (warp >> 3) is warps (w, w + 4) and wb = (warp >> 2) & 1 tells them apart.
+    static_assert(!SM::kXTm || TEAMS == 8, "the tensor-memory exchange pairs warps (w, w + 4) of a 16-warp CTA");
+#if defined(PEBA1_ABLATE) && PEBA1_ABLATE == 5  /* what-if: the tensor-memory exchange code with teams of ADJACENT warps (wrong data) */
+    const int wb = warp & 1;
+    const int team = (int)(threadIdx.x / kTeam);
+#else
+    const int wb = SM::kXTm ? (warp >> 2) & 1 : warp & 1;
+    const int team = SM::kXTm ? (warp & 3) + 4 * (warp >> 3) : (int)(threadIdx.x / kTeam);
+#endif
+    const int team_tid = 32 * wb + (int)(threadIdx.x & 31);
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"l"(
             (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    if ((threadIdx.x % kTeam) == 0) {
+    if (team_tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"((uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    DevEnvTm env{(int)(threadIdx.x % kTeam), team + 1, kTmSums + 64 * (warp >> 2),
+    DevEnvTm env{team_tid, team + 1, kTmSums + 64 * (warp >> 2),
                  tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16)};
     env.ex1_mbar = (uint32_t)__cvta_generic_to_shared(&teams[team].ex1_free);
     env.tv_col = SM::kTv + 16 * (warp >> 2);
     env.own_col = SM::kOwn + 32 * (warp >> 2);
-    if (SM::kXTm) {  // WHAT-IF wiring (the partner sits in another lane quarter here): costs right, data wrong
-        env.x_col = SM::kX + 32 * (warp >> 2);
-        env.x_peer = SM::kX + 32 * ((warp >> 2) ^ 1);
-        env.x_half = warp & 1;
-    }
-    if ((warp >> 2) == 0) {  // one warp per lane quarter publishes the per-thread twiddles
+    if constexpr (SM::kXTm) {
+        const int lane = (int)(threadIdx.x & 31);
+        // twiddles: tw1 belongs to tid = 32 wb + lane (one set per wb: warps 0..7 publish), tw2 to lo = lane >> 2 (warps 0..3)
+        if (warp < 8) {
+            double2 t1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t1[j] = c_tables.tw1[team_tid][j];
+            tm_store8(env, env.tw1_col(), t1);
+        }
+        if (warp < 4) {
+            double2 t2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t2[j] = c_tables.tw2[lane >> 2][j];
+            tm_store8(env, SM::kTw2, t2);
+        }
+        env.tmem_wait_st();
+    } else if ((warp >> 2) == 0) {  // one warp per lane quarter publishes the per-thread twiddles
         TeamTwiddles tw;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -1291,6 +1317,22 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         return 0;
     }
 #endif  // PEBA1_ALL_VARIANTS
+#ifdef PEBA1_ALL_VARIANTS
+    if (c->kernel_variant == 12 &&
+        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * 6)) {
+        // WHAT-IF (timing only until the exchange indices are wired): variant 9 (6 teams, MAC accumulators in registers) with
+        // the cross-team exchange through tensor memory
+        constexpr int T6 = 6;
+        const size_t smem = sizeof(TeamSmemTmX) * (size_t)T6;
+        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
+        const unsigned grid = std::min((unsigned)((count + T6 - 1) / T6), (unsigned)c->sm_count);
+        auto k = pbs_kernel_tm<L, BGBIT, T6, TeamSmemTmX, true>;
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, T6 * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
+        return 0;
+    }
+#endif
     if (c->kernel_variant == 8 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // two alternating exchange buffers without the "buffer free" mbarrier (TeamSmemTm2): what the default does for
@@ -2262,7 +2304,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 11) return fail(PEBA1_EINVAL, "kernel_variant must be 0..11");
+        if (value < 0 || value > 12) return fail(PEBA1_EINVAL, "kernel_variant must be 0..12");
 #ifndef PEBA1_ALL_VARIANTS
         if (value != 1 && value != 7 && value != 8 && value != 11)
             return fail(PEBA1_EINVAL, "kernel_variant %lld lost against the default and is not compiled into this build "

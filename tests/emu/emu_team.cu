@@ -73,6 +73,37 @@ struct HostEnv {
     // split-phase "exchange buffer free" barrier of the device code: a full team barrier is a valid (stronger) stand-in
     void ex1_acquire() { pthread_barrier_wait(team); }
     void ex1_release() {}
+    // ---- the cross-team exchange through tensor memory (TeamSmemTmX): the two 32-lane x 32-column blocks of a team and
+    // the fragment layout of tcgen05.ld/st.16x256b.x2 as the device probe (scripts/ubench/tmem_xchg_probe.cu) printed it:
+    // thread t, register j of the access at lane half H: lane (t >> 2) + 8 ((j >> 1) & 1) + 16 H, column 8 (j >> 2) + 2 (t & 3) + (j & 1)
+    uint32_t (*xt)[32][32] = nullptr;  // [block = the team's warp][lane][column]
+    int wb = 0, tw1_col_ = 0, xhi_ = 0, xlo_ = 0;
+    int tw1_col() const { return tw1_col_; }
+    int xhi() const { return xhi_; }
+    int xlo() const { return xlo_; }
+    void xtm_exchange_fwd(uint32_t (&v)[32]) {
+        const int t = tid & 31;
+        pthread_barrier_wait(team);
+        memcpy(xt[wb][t], v, sizeof v);
+        pthread_barrier_wait(team);
+        for (int q = 0; q < 4; ++q) {
+            const int S = q >> 1, H = q & 1;
+            for (int j = 0; j < 8; ++j)
+                v[8 * q + j] = xt[S][(t >> 2) + 8 * ((j >> 1) & 1) + 16 * H][16 * wb + 8 * (j >> 2) + 2 * (t & 3) + (j & 1)];
+        }
+    }
+    void xtm_exchange_inv(uint32_t (&v)[32], uint32_t (&tw)[32]) {
+        const int t = tid & 31;
+        pthread_barrier_wait(team);
+        for (int q = 0; q < 4; ++q) {
+            const int S = q >> 1, H = q & 1;
+            for (int j = 0; j < 8; ++j)
+                xt[S][(t >> 2) + 8 * ((j >> 1) & 1) + 16 * H][16 * wb + 8 * (j >> 2) + 2 * (t & 3) + (j & 1)] = v[8 * q + j];
+        }
+        pthread_barrier_wait(team);
+        memcpy(v, xt[wb][t], sizeof v);
+        memcpy(tw, tm + tw1_col_, sizeof tw);
+    }
 };
 
 struct Shared {
@@ -81,6 +112,8 @@ struct Shared {
     TeamSmemTm1 sm_tm1;
     TeamSmemTm2 sm_tm2;
     TeamSmemTm2S sm_tm2s;
+    TeamSmemTmX sm_tmx;
+    uint32_t xt[2][32][32];
     double2 shfl_slots[2][32];
     TeamSmemPair sm_pair;
     TwiddleTables tables;
@@ -150,6 +183,28 @@ void* worker(void* p) {
                 blind_rotate_team_tm<3, 7>(env, S->sm_tm2s, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
             else
                 blind_rotate_team_tm<2, 10>(env, S->sm_tm2s, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
+        }
+    } else if (S->mode == 9) {
+        // cross-team exchange through tensor memory: tid = 32 wb + lane; twiddles as the kernel publishes them
+        std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
+        env.tm = tmem.data();
+        env.sums_col = 64 * (A->tid % 4);
+        env.xt = S->xt;
+        env.wb = A->tid >> 5;
+        env.tw1_col_ = TeamSmemTmX::kTw1 + 32 * env.wb;
+        env.xhi_ = 4 * env.wb + (A->tid & 3);
+        env.xlo_ = (A->tid & 31) >> 2;
+        tm_store8(env, env.tw1_col_, tw.tw1);
+        double2 t2[8];
+        for (int j = 0; j < 8; ++j) t2[j] = S->tables.tw2[env.xlo_][j];
+        tm_store8(env, TeamSmemTmX::kTw2, t2);
+        for (int64_t g = 0; g < S->count; ++g) {
+            PbsJob job{(int32_t)g, -1, 0, 1, 0};
+            int32_t* u = S->u_out + (size_t)g * (kN + 1);
+            if (S->L == 3 && S->Bgbit == 7)
+                blind_rotate_team_tm<3, 7>(env, S->sm_tmx, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
+            else
+                blind_rotate_team_tm<2, 10>(env, S->sm_tmx, S->bkfft, S->n, S->in_ct, S->n + 1, job, u);
         }
     } else if (S->mode == 5) {
         std::vector<uint32_t> tmem(512, 0xDEADBEEFu);
@@ -409,6 +464,18 @@ int peba1_emu_bootstrap_woks_tm2s(int L, int Bgbit, int n, const double* bkfft, 
     if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
     Shared* S = new Shared();
     S->mode = 8; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
+    S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
+    int rc = run(S);
+    delete S;
+    return rc;
+}
+
+// TeamSmemTmX: the cross-team exchange of every transform through tensor memory (kernel_variant 11)
+int peba1_emu_bootstrap_woks_tmx(int L, int Bgbit, int n, const double* bkfft, const int32_t* in_ct, int32_t* u_out,
+                                 int64_t count) {
+    if (!((L == 3 && Bgbit == 7) || (L == 2 && Bgbit == 10))) return -1;
+    Shared* S = new Shared();
+    S->mode = 9; S->L = L; S->Bgbit = Bgbit; S->n = n; S->rows = 2 * L;
     S->bkfft = (double2*)bkfft; S->in_ct = in_ct; S->u_out = u_out; S->count = count;
     int rc = run(S);
     delete S;

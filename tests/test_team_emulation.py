@@ -93,6 +93,9 @@ def test_other_variants_match_exact_oracle_on_a_short_key(emu, oracle):
         assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm, tin), want)
         # the inner exchange by warp shuffles (lane8_transpose; kernel_variant 10)
         assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tm2s, tin[1:]), want[1:])
+        # the cross-team exchange through tensor memory (TeamSmemTmX; kernel_variant 11): warps (w, w + 4) as a team, the
+        # 16x256b fragment layout, the permuted logical thread positions and the re-swizzled inner exchange
+        assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_tmx, tin), want)
         # the low-latency kernel does not skip void steps (all-zero digits instead): ciphertext 1 exercises that, and
         # three jobs in a row the re-use of the key-row pipeline across jobs
         assert np.array_equal(run(emu.peba1_emu_bootstrap_woks_wide, tin), want)
@@ -115,7 +118,7 @@ def test_second_parameter_set_on_a_short_key(emu, oracle):
     try:
         want = np.stack([K.bootstrap_woks(t, mode=oracle.EXACT) for t in tin])
         for fn in (emu.peba1_emu_bootstrap_woks, emu.peba1_emu_bootstrap_woks_tm, emu.peba1_emu_bootstrap_woks_tm2,
-                   emu.peba1_emu_bootstrap_woks_tm2s, emu.peba1_emu_bootstrap_woks_wide):
+                   emu.peba1_emu_bootstrap_woks_tm2s, emu.peba1_emu_bootstrap_woks_tmx, emu.peba1_emu_bootstrap_woks_wide):
             u = np.zeros((2, 1025), dtype=np.int32)
             assert fn(2, 10, n, bkfft.ctypes.data_as(C.c_void_p), tin.ctypes.data_as(C.c_void_p),
                       u.ctypes.data_as(C.c_void_p), C.c_int64(2)) == 0
