@@ -203,9 +203,26 @@ void store_word(LweSample* out, const Word& w, int bits) {
     for (int i = 0; i < bits; ++i) w[i].store(&out[i]);
 }
 
+[[noreturn]] void bad_size(const char* routine, const char* what, int bitsize, int width) {
+    // The reference overruns its heap arrays in these cases (Math.cpp:216 hard-codes 23 result samples, :337 24 accumulator
+    // samples); a drop-in must not turn that into silent undefined behaviour of its own.
+    fprintf(stderr, "peba1: fatal: %s: %s (bitsize %d, width %d)\n", routine, what, bitsize, width);
+    abort();
+}
+
 int multiply_width(int bitsize, int width) {
-    if (width > 0) return width;
-    return 23;  // the reference's hard-coded length (Math.cpp:216); valid for bitsize <= 12
+    if (bitsize < 1) bad_size("bootsMultiply", "bitsize must be positive", bitsize, width);
+    const int w = width > 0 ? width : 23;  // the reference's hard-coded length (Math.cpp:216)
+    // partial product i touches result samples i .. i + bitsize - 1: the last needs 2 * bitsize - 1 samples
+    if (2 * bitsize - 1 > w) bad_size("bootsMultiply", "the product needs 2 * bitsize - 1 samples, more than the result width", bitsize, w);
+    return w;
+}
+
+// the distance circuits accumulate on 23 samples (24 allocated), squares of (bitsize + 1)-bit differences: bitsize 8 in
+// the reference (main.cpp:20 `bitsize = 8`); anything that makes the multiplier or the 3 * bitsize comparator index
+// outside those arrays is refused
+void check_distance_bitsize(const char* routine, int bitsize) {
+    if (bitsize < 8 || 2 * bitsize - 1 > 23) bad_size(routine, "bitsize must be 8..12 (23-sample accumulator, 3 * bitsize >= 24 comparator)", bitsize, 23);
 }
 
 void check_vectors(const char* what, size_t na, size_t nb) {
@@ -403,6 +420,7 @@ void peba1_math_euclidean(LweSample* result, LweSample* const* a, LweSample* con
     RoutineScope scope(bk);
     Builder B{scope.e};
     // reference HE_EuclideanDistance (Math.cpp:333-369): the caller's `result` is the running sum (read first)
+    check_distance_bitsize("HE_EuclideanDistance", bitsize);
     Word acc = B.load(result, 24);
     euclid_into(B, acc, a, b, slots, bitsize);
     store_word(result, acc, 23);  // bit 23 is never written (Q5)
@@ -417,8 +435,9 @@ void peba1_math_function_f(LweSample* result_b, LweSample* const* a, LweSample* 
     Builder B{scope.e};
     // reference Function_f (Math.cpp:379-387): the distance accumulator is a fresh allocation, defined here as
     // trivial false (Q2); comparator bit = 1 iff distance > bound (Q3)
+    check_distance_bitsize("Function_f", bitsize);
     const int nb = bitsize * 3;
-    Word ed((size_t)nb, Bit::constant(false));
+    Word ed((size_t)std::max(nb, 24), Bit::constant(false));
     euclid_into(B, ed, a, b, slots, bitsize);
     Word mn;
     const Bit c = B.minimum(ed, B.load(bound_match, nb), nb, mn);

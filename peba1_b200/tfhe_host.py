@@ -51,7 +51,8 @@ class TestBackend(C.Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "host", "libpeba1_tfhe.so")
+    # PEBA1_TFHE_LIB: an instrumented build of the same sources (scripts/sanitize_host.sh: ASan + UBSan)
+    return os.environ.get("PEBA1_TFHE_LIB") or os.path.join(_HERE, "host", "libpeba1_tfhe.so")
 
 
 def load_library():

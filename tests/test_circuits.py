@@ -537,3 +537,19 @@ def test_random_gate_dags_decrypt_the_same_in_every_mode(env, mode):
             assert got == val, (m, trial)
             ks.free_array(nin + nnodes, arr)
     L.peba1_set_mode(0)
+
+
+def test_out_of_range_sizes_are_refused_not_overrun():
+    """The reference overruns its 23-sample product / 24-sample accumulator arrays for larger operands (Math.cpp:216, :337);
+    the drop-in aborts with a message instead (upstream's own convention for fatal errors)."""
+    import subprocess
+    import sys
+    code = ("import ctypes as C, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from peba1_b200 import tfhe_host as H\nfrom sim_backend import SimBackend\n"
+            "L = H.load_library(); sim = SimBackend(); sim.install(); ks = H.KeySet.generate(128, seed=7); sim.keyset = ks\n"
+            "a, b, r = ks.new_array(16), ks.new_array(16), ks.new_array(48)\n"
+            "L.peba1_math_multiply(r, a, b, 13, 0, ks.cloud)\n") % (
+        __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))),
+        __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode != 0 and "needs 2 * bitsize - 1 samples" in out.stderr
