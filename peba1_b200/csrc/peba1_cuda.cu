@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(TEAMS* kTeam, 1)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (job_counter == nullptr) {  // one job per team, fixed by the grid
-        const int64_t g = (int64_t)blockIdx.x * TEAMS + team;
+        // (the narrow shapes launch this same instantiation with fewer teams per CTA: blockDim.x / 64 of them)
+        const int64_t g = (int64_t)blockIdx.x * (int64_t)(blockDim.x / kTeam) + team;
         if (g < count)
             blind_rotate_team_tm<L, BGBIT>(env, teams[team], bkfft, n, pool, pool_stride, jobs[g],
                                            u_out + g * (int64_t)kUStride);
@@ -717,8 +718,46 @@ __global__ void __launch_bounds__(256)
 }
 
 // K0+K1, low-latency version (blind_rotate_wide.cuh): one CTA of 2l teams per bootstrap, for narrow circuit levels.
-struct DevEnvWide : DevEnv {
+struct DevEnvWide : DevEnvTm {
     __device__ __forceinline__ void cta_sync() const { __syncthreads(); }
+    __device__ __forceinline__ void cta_sync_tm() const {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    // a team's 16 partial products <-> the 64 tensor-memory columns of its warp (block = warp / 4; thread = lane), moved in
+    // pieces of 4 values: a 32- or 64-register staging vector next to the 64 twiddle registers makes ptxas rematerialise the
+    // twiddles from constant memory inside the step loop (thread-indexed LDC: 6.9 ms instead of 2.5, ncu r2h)
+    __device__ __forceinline__ void prod_store(const double2 (&p0)[8], const double2 (&p1)[8]) const {
+        const uint32_t col = 64u * (uint32_t)(threadIdx.x >> 7);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = h < 2 ? p0[4 * h + k] : p1[4 * (h - 2) + k];
+                c_to_words(v, w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+            }
+            tmem_st_x16(tm_base + col + 16u * (uint32_t)h, w);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    // p0, p1 += the products of team r (same parity as the caller's team: its warps sit in the caller's lane quarters)
+    __device__ __forceinline__ void prod_accumulate(int r, double2 (&p0)[8], double2 (&p1)[8]) const {
+        const uint32_t col = 64u * (uint32_t)((2 * r + (int)((threadIdx.x >> 5) & 1)) >> 2);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            uint32_t w[16];
+            tmem_ld_x16(tm_base + col + 16u * (uint32_t)h, w);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 v = words_to_c(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+                if (h < 2) p0[4 * h + k] = cadd(p0[4 * h + k], v);
+                else p1[4 * (h - 2) + k] = cadd(p1[4 * (h - 2) + k], v);
+            }
+        }
+    }
     __device__ __forceinline__ void pair_sync() const { asm volatile("bar.sync 15, 128;" ::: "memory"); }
     __device__ __forceinline__ void key_fetch(void* dst, const void* src, unsigned bytes, unsigned long long* mbar) const {
         const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst), b = (uint32_t)__cvta_generic_to_shared(mbar);
@@ -744,23 +783,49 @@ __global__ void __launch_bounds__(2 * L * kTeam, 1)
                     const PbsJob* __restrict__ jobs, int64_t count, int32_t* __restrict__ u_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WideSmem<2 * L>& sm = *reinterpret_cast<WideSmem<2 * L>*>(smem_raw);
+    __shared__ uint32_t tm_alloc_base;
     const int team = threadIdx.x / kTeam;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {  // 64 columns per warp of a lane quarter, up to 3 warps per quarter: 256 allocated
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"l"(
+            (uint64_t)__cvta_generic_to_shared(&tm_alloc_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     DevEnvWide env;
     env.tid = (int)(threadIdx.x % kTeam);
     env.bar_id = team + 1;
-    TeamTwiddles tw;
-    load_twiddles_dev(env.tid, tw);
+    env.tm_base = tm_alloc_base + ((uint32_t)(warp & 3) * 32u << 16);
+    if (warp < 4) {  // one warp per lane quarter publishes the twiddles of tid = 32 (warp & 1) + lane
+        double2 t1[8], t2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            t1[j] = c_tables.tw1[env.tid][j];
+            t2[j] = c_tables.tw2[env.tid & 7][j];
+        }
+        tm_store8(env, kWideTw1, t1);
+        tm_store8(env, kWideTw2, t2);
+        env.tmem_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int64_t g = blockIdx.x; g < count; g += gridDim.x) {
         if (env.tid == 0) {  // a fresh barrier per job: the parity of step i is i & 1
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sm.key_full[team])));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        blind_rotate_wide<L, BGBIT>(env, sm, tw, team, bkfft, n, pool, pool_stride, jobs[g], u_out + g * (int64_t)kUStride);
+        blind_rotate_wide<L, BGBIT>(env, sm, team, bkfft, n, pool, pool_stride, jobs[g], u_out + g * (int64_t)kUStride);
         __syncthreads();  // the shared accumulator is reused by the CTA's next job
         if (env.tid == 0)  // the next job initialises the barrier again: a live mbarrier must be invalidated first
             asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&sm.key_full[team])) : "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tm_alloc_base));
 }
 
 // K3.  One team per key polynomial q = (i*rows + r)*2 + c.
@@ -1171,7 +1236,7 @@ struct peba1_cuda_ctx {
     // options
     int teams_per_cta = 6;
     int tm_teams = 0;        // teams per CTA of the tensor-memory kernel; 0 = by batch size
-    int narrow_two_buffers = 0;  // 1: the narrow shapes (fixed grids of 1..8 teams) run on TeamSmemTm2 as well (not measured yet)
+    int narrow_two_buffers = 1;  // the narrow shapes (fixed grids of 1..8 teams) run on TeamSmemTm2 as well; 0 needs VARIANTS=all
     int ks_group = 1;        // ciphertexts per keyswitch CTA (measured: 1 is fastest, the L1 pipe is the bound)
     int ks_tile = 0;         // ciphertexts per group of the tiled keyswitch (8, 12, 16; 0 = off), 2 groups per CTA
     int ks_tile_parts = 1;   // CTAs per tile (coefficient ranges, partial sums by red.global.add)
@@ -1257,21 +1322,30 @@ int launch_pbs_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const P
 }
 
 #endif  // PEBA1_ALL_VARIANTS
+// narrow shapes: fixed grid, TEAMS (1..8) teams per CTA.  Three instantiations serve them — compiled for 2, 4 and 8 teams
+// (launch bounds of 128 / 256 / 512 threads: with one or two warps per scheduler ptxas needs the registers beyond 128 to
+// schedule for latency; the 8-team build measured 7.1 ms instead of 4.6 for 296 bootstraps) — each launched with
+// TEAMS * 64 threads and TEAMS team areas of shared memory.
 template <int L, int BGBIT, int TEAMS, class SM>
 int launch_pbs_tm_ts(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
                      int32_t* u) {
+    constexpr int BUILT = TEAMS <= 2 ? 2 : TEAMS <= 4 ? 4 : kTeamsTm;
     const size_t smem = sizeof(SM) * (size_t)TEAMS;
     const unsigned grid = (unsigned)((count + TEAMS - 1) / TEAMS);
-    auto k = pbs_kernel_tm<L, BGBIT, TEAMS, SM>;
-    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto k = pbs_kernel_tm<L, BGBIT, BUILT, SM>;
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(SM) * (size_t)BUILT)));
     k<<<grid, TEAMS * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, nullptr);
     return 0;
 }
 template <int L, int BGBIT, int TEAMS>
 int launch_pbs_tm_t(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const PbsJob* jobs, int64_t count,
                     int32_t* u) {
-    return c->narrow_two_buffers ? launch_pbs_tm_ts<L, BGBIT, TEAMS, TeamSmemTm2>(c, pool, stride, jobs, count, u)
-                                 : launch_pbs_tm_ts<L, BGBIT, TEAMS, TeamSmemTm>(c, pool, stride, jobs, count, u);
+    // the narrow shapes run on the two-buffer layout too (measured r2g, kbench: 296 bootstraps 4.72 -> 4.55 ms, 1,036:
+    // 10.63 -> 10.33 ms, 648: 8.33 = 8.33 ms); the one-buffer layout with its "buffer free" mbarrier is a VARIANTS=all build
+#ifdef PEBA1_ALL_VARIANTS
+    if (!c->narrow_two_buffers) return launch_pbs_tm_ts<L, BGBIT, TEAMS, TeamSmemTm>(c, pool, stride, jobs, count, u);
+#endif
+    return launch_pbs_tm_ts<L, BGBIT, TEAMS, TeamSmemTm2>(c, pool, stride, jobs, count, u);
 }
 
 template <int L, int BGBIT>
@@ -1372,6 +1446,7 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         return 0;
     }
 #endif  // PEBA1_ALL_VARIANTS
+#ifdef PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 7 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // persistent 8-team CTAs on the single cross-team exchange buffer with its "buffer free" mbarrier (TeamSmemTm): the
@@ -1385,6 +1460,7 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         k<<<grid, kTeamsTm * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
         return 0;
     }
+#endif
 #ifdef PEBA1_ALL_VARIANTS
     if (c->kernel_variant == 4 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
@@ -1419,10 +1495,10 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
                                                                      c->d_job_counter);
         return 0;
     }
-    // Very narrow level (at most one bootstrap per SM): latency matters, not throughput — one CTA of 2l teams per
-    // bootstrap, 2.5 ms against 4.6 ms for a lone team.  Beyond one wave the throughput kernel's narrow shapes win
-    // (measured, scripts/prof_mid.py: 296 -> 4.8 ms with T=2 vs 4.9; 444 -> 5.9 ms with T=4 vs 7.4).
-    const bool wide = c->wide_max_batch < 0 ? count <= c->sm_count : count <= c->wide_max_batch;
+    // Very narrow level (at most two bootstraps per SM): latency matters, not throughput — one CTA of 2l teams per
+    // bootstrap, 2.17 ms per wave of up to 148 against 4.5 ms for a lone team.  Two waves (4.34 ms) still beat the
+    // throughput kernel's T = 2 shape (4.57 ms for 296); from three waves on the narrow shapes below win (444: 5.4 ms).
+    const bool wide = c->wide_max_batch < 0 ? count <= 2 * (int64_t)c->sm_count : count <= c->wide_max_batch;
     if (c->kernel_variant == 1 && c->tm_teams == 0 && wide) {
         const size_t smem = sizeof(WideSmem<2 * L>);
         const unsigned grid = (unsigned)std::min<int64_t>(count, (int64_t)c->sm_count * 4);
@@ -1509,7 +1585,8 @@ int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t co
         c->stats.keyswitches += (uint64_t)count;
         return 0;
     }
-    // wide level: the tiled kernel (key streamed once per tile of ciphertexts)
+#ifdef PEBA1_ALL_VARIANTS
+    // wide level: the tiled kernel (key streamed once per tile of ciphertexts) — measured slower (profiles/r2c), VARIANTS=all
     if (c->ks_tile > 0 && count >= (int64_t)c->ks_tile_min) {
         const int parts = c->ks_tile_parts;
         const int64_t per_cta = 2 * c->ks_tile;
@@ -1526,12 +1603,15 @@ int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t co
         c->stats.keyswitches += (uint64_t)count;
         return 0;
     }
+#endif
     const unsigned grid = (unsigned)((count + G - 1) / G);
     switch (G) {
+#ifdef PEBA1_ALL_VARIANTS  // several ciphertexts per CTA: measured no gain
         case 2: keyswitch_kernel<8, 2, 2><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
         case 4: keyswitch_kernel<8, 2, 4><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
         case 8: keyswitch_kernel<8, 2, 8><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
         case 6: keyswitch_kernel<8, 2, 6><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
+#endif
         default: keyswitch_kernel<8, 2, 1><<<grid, kKsThreads, 0, c->stream>>>(c->ksk, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, pool); break;
     }
     CU(cudaGetLastError());
@@ -2267,12 +2347,18 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
     }
     if (!strcmp(name, "ks_group")) {
         if (value == 0) value = 1;
+#ifndef PEBA1_ALL_VARIANTS
+        if (value != 1) return fail(PEBA1_EINVAL, "ks_group > 1 measured no gain and is not compiled into this build (make VARIANTS=all)");
+#endif
         if (value != 1 && value != 2 && value != 4 && value != 6 && value != 8) return fail(PEBA1_EINVAL, "ks_group must be 1, 2, 4, 6 or 8");
         c->ks_group = (int)value;
         return 0;
     }
     if (!strcmp(name, "ks_tile")) {
         if (value != 0 && value != 8 && value != 12 && value != 16) return fail(PEBA1_EINVAL, "ks_tile must be 0, 8, 12 or 16");
+#ifndef PEBA1_ALL_VARIANTS
+        if (value != 0) return fail(PEBA1_EINVAL, "the tiled keyswitch measured slower and is not compiled into this build (make VARIANTS=all)");
+#endif
         c->ks_tile = (int)value;
         return 0;
     }
@@ -2306,7 +2392,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
     if (!strcmp(name, "kernel_variant")) {
         if (value < 0 || value > 12) return fail(PEBA1_EINVAL, "kernel_variant must be 0..12");
 #ifndef PEBA1_ALL_VARIANTS
-        if (value != 1 && value != 7 && value != 8 && value != 11)
+        if (value != 1 && value != 8 && value != 11)
             return fail(PEBA1_EINVAL, "kernel_variant %lld lost against the default and is not compiled into this build "
                                       "(make -C peba1_b200/csrc VARIANTS=all)", (long long)value);
 #endif

@@ -287,6 +287,7 @@ struct WideShared {
     TwiddleTables tables;
     pthread_barrier_t cta, pair, team[ROWS], warp[2 * ROWS];
     std::atomic<int> fetched[ROWS];  // key rows that have "landed" per team: stands in for the TMA mbarrier
+    double2 prod[ROWS][kTeam][16];    // the teams' tensor-memory columns with their partial products
     int n;
     const double2* bkfft;
     const int32_t* in_ct;
@@ -299,6 +300,13 @@ struct WideEnv : HostEnv {
     int my_team;
     int waited = 0;  // key rows this thread has consumed
     void cta_sync() { pthread_barrier_wait(&S->cta); }
+    void cta_sync_tm() { pthread_barrier_wait(&S->cta); }
+    void prod_store(const double2 (&p0)[8], const double2 (&p1)[8]) {
+        for (int k = 0; k < 8; ++k) { S->prod[my_team][tid][k] = p0[k]; S->prod[my_team][tid][8 + k] = p1[k]; }
+    }
+    void prod_accumulate(int r, double2 (&p0)[8], double2 (&p1)[8]) {
+        for (int k = 0; k < 8; ++k) { p0[k] = cadd(p0[k], S->prod[r][tid][k]); p1[k] = cadd(p1[k], S->prod[r][tid][8 + k]); }
+    }
     void pair_sync() { pthread_barrier_wait(&S->pair); }
     // the device issues an asynchronous bulk copy that completes on the mbarrier; here the copy is done on the spot and
     // published by a release increment, and key_wait spins until as many rows have landed as this thread has asked for
@@ -327,9 +335,13 @@ void* wide_worker(void* p) {
     env.my_team = team;
     TeamTwiddles tw;
     load_team_twiddles(S->tables, tid, tw);
+    std::vector<uint32_t> tmem(512, 0xDEADBEEFu);  // the thread's view of its lane's twiddle columns
+    env.tm = tmem.data();
+    tm_store8(env, kWideTw1, tw.tw1);
+    tm_store8(env, kWideTw2, tw.tw2);
     for (int64_t g = 0; g < S->count; ++g) {
         PbsJob job{(int32_t)g, -1, 0, 1, 0};
-        blind_rotate_wide<L, BGBIT>(env, S->sm, tw, team, S->bkfft, S->n, S->in_ct, S->n + 1, job,
+        blind_rotate_wide<L, BGBIT>(env, S->sm, team, S->bkfft, S->n, S->in_ct, S->n + 1, job,
                                     S->u_out + (size_t)g * (kN + 1));
         env.cta_sync();  // the kernel's job loop: nobody starts the next prologue before the outputs are written
     }

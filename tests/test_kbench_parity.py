@@ -63,6 +63,6 @@ def test_gpu_checksums_equal_the_oracle_at_full_size():
     k = _kbench_bin()
     want = GOLD["batch=16384 op=0"]["oracle"]
     assert _checksum([k, "batch=16384", "steps=1", "warmup=0"]) == want
-    assert _checksum([k, "batch=16384", "steps=1", "warmup=0", "kernel_variant=7"]) == want
+    assert _checksum([k, "batch=16384", "steps=1", "warmup=0", "kernel_variant=8"]) == want
     assert _checksum([k, "batch=81", "steps=1", "warmup=0"]) == GOLD["batch=81 op=0"]["oracle"]
     assert _checksum([k, "batch=16384", "op=10", "steps=1", "warmup=0"]) == GOLD["batch=16384 op=10"]["oracle"]  # bootsMUX
