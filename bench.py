@@ -543,7 +543,7 @@ def main():
                      "kernel": "pbs_kernel_tm (blind rotation)", "kernel_ms": br_ms,
                      "peak_source": "DFMA probe run live on this GPU by this process (peba1_cuda_measure_fp64_peak: 8 independent "
                                     "DFMA chains per thread on every SM); MEASURED_PEAKS.json and the profiling guide have no "
-                                    "FP64 entry; scripts/ubench/fp64_rates.cu is the stand-alone probe (profiles/r2_fp64_rates.log)",
+                                    "FP64 entry; scripts/ubench/fp64_rates.cu is the stand-alone probe (profiles/r2j_fp64_rates.log)",
                      "peak_nominal": FP64_PEAK_NOMINAL, "frac_nominal": achieved_tf / FP64_PEAK_NOMINAL,
                      "traffic_source": NCU_SOURCE["blind_rotate"],
                      "note": "dominant kernel = blind rotation (FP64 vector pipe; neither hbm nor tensor applies). "

@@ -37,6 +37,18 @@ def test_oracle_reproduces_the_gpu_checksum_of_a_narrow_level():
     assert got == GOLD["batch=81 op=0"]["gpu"]
 
 
+def test_exact_integer_oracle_rederives_a_recorded_checksum():
+    """The `oracle_exact` entries are not just recorded: here the oracle's EXACT-INTEGER form (O(N^2) negacyclic products, no
+    floating point) recomputes the 200-gate batch — two waves of the low-latency kernel on the GPU — and must print the
+    checksum the GPU printed (about 30 s on 8 cores); the FP64-FFT form does the mid-size shapes in seconds."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "kbench"])
+    o = os.path.join(UB, "kbench_oracle_bin")
+    threads = f"threads={os.cpu_count() or 1}"
+    assert _checksum([o, "batch=200", threads, "mode=0"]) == GOLD["batch=200 op=0"]["gpu"]
+    assert _checksum([o, "batch=648", threads]) == GOLD["batch=648 op=0"]["gpu"]
+    assert _checksum([o, "batch=1036", threads]) == GOLD["batch=1036 op=0"]["gpu"]
+
+
 @pytest.mark.skipif(os.environ.get("PEBA1_SLOW") != "1", reason="two minutes on 8 cores; PEBA1_SLOW=1 runs it")
 def test_oracle_reproduces_the_gpu_checksum_at_full_size():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "kbench"])
@@ -65,4 +77,6 @@ def test_gpu_checksums_equal_the_oracle_at_full_size():
     assert _checksum([k, "batch=16384", "steps=1", "warmup=0"]) == want
     assert _checksum([k, "batch=16384", "steps=1", "warmup=0", "kernel_variant=8"]) == want
     assert _checksum([k, "batch=81", "steps=1", "warmup=0"]) == GOLD["batch=81 op=0"]["oracle"]
+    for n in (200, 648, 1036):   # two waves of the low-latency kernel; narrow shapes of 5 and 7 teams per CTA
+        assert _checksum([k, f"batch={n}", "steps=1", "warmup=0"]) == GOLD[f"batch={n} op=0"]["oracle"], n
     assert _checksum([k, "batch=16384", "op=10", "steps=1", "warmup=0"]) == GOLD["batch=16384 op=10"]["oracle"]  # bootsMUX
