@@ -42,6 +42,21 @@ PEBA1_HD int32_t rot_only(const int32_t* acc, int j, int abar) {
     return (idx & kN) ? (int32_t)(0u - (uint32_t)v) : v;
 }
 
+// K0, shared by every blind-rotation variant: gate prologue t = (0, c0) + s0 pool[in0] + s1 pool[in1] (+ s2 pool[in2]) and
+// mod-switch to Z_2N, bar = ((uint32)t + 2^20) >> 21, written to `bara[0..n]` by `nthreads`
+// threads (index `t0`).  The caller synchronises afterwards.
+template <class Env>
+PEBA1_HD void gate_prologue_modswitch(Env& env, uint16_t* bara, int n, const int32_t* __restrict__ pool, int64_t pool_stride,
+                                      const PbsJob& job, int t0, int nthreads) {
+    for (int w = t0; w <= n; w += nthreads) {
+        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
+        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
+        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
+        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
+        bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
+    }
+}
+
 // L = gadget length, BGBIT = log2 of the gadget base.  `u_out` receives the extracted sample (N+1 words).
 template <int L, int BGBIT, class Env>
 PEBA1_HD void blind_rotate_team(Env& env, TeamSmem& sm, const TeamTwiddles& tw, const double2* __restrict__ bkfft,
@@ -56,13 +71,7 @@ PEBA1_HD void blind_rotate_team(Env& env, TeamSmem& sm, const TeamTwiddles& tw, 
     const int tid = env.tid;
 
     // ---- K0: prologue + mod-switch to Z_2N: bar = ((uint32)t + 2^20) >> 21
-    for (int w = tid; w <= n; w += kTeam) {
-        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
-    }
+    gate_prologue_modswitch(env, sm.bara, n, pool, pool_stride, job, tid, kTeam);
     env.team_sync();
 
     // ---- step 3: ACC = (0, X^(2N - barb) * (mu, ..., mu)), mu = 1/8

@@ -149,13 +149,7 @@ PEBA1_HD void blind_rotate_pair_tm(Env& env, TeamSmemPair& sm, const double2* __
 #pragma unroll 1
     for (int ct = 0; ct < 2; ++ct) {
         const PbsJob job = ct ? job1 : job0;
-        for (int w = tid; w <= n; w += kTeam) {
-            uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-            if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-            if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-            if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-            sm.bara[ct][w] = (uint16_t)((t + (1u << 20)) >> 21);
-        }
+        gate_prologue_modswitch(env, sm.bara[ct], n, pool, pool_stride, job, tid, kTeam);
     }
     env.team_sync();
 #pragma unroll 1

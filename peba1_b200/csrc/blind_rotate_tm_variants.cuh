@@ -25,13 +25,7 @@ PEBA1_HD void blind_rotate_team_tmr(Env& env, SM& sm, const double2* __restrict_
     const int sums = env.sums_col;  // kTmSums + 64 * (warp / 4)
 
     // ---- prologue + mod-switch (identical to blind_rotate_team)
-    for (int w = tid; w <= n; w += kTeam) {
-        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
-    }
+    gate_prologue_modswitch(env, sm.bara, n, pool, pool_stride, job, tid, kTeam);
     env.team_sync();
     {
         const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);
@@ -159,13 +153,7 @@ PEBA1_HD void blind_rotate_team_tmsh(Env& env, TeamSmemTm& sm, const double2* __
     const int sums = env.sums_col;
     const int myq = env.chunk_id;  // which quarter of every key row this team fetches: q = (column c, half)
 
-    for (int w = tid; w <= n; w += kTeam) {
-        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
-    }
+    gate_prologue_modswitch(env, sm.bara, n, pool, pool_stride, job, tid, kTeam);
     env.team_sync();
     {
         const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);

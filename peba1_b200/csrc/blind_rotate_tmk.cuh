@@ -50,13 +50,7 @@ PEBA1_HD void blind_rotate_team_tmk(Env& env, TeamSmemTm& sm, int n, const int32
     const int tid = env.tid;
     const int sums = env.sums_col;
 
-    for (int w = tid; w <= n; w += kTeam) {
-        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
-    }
+    gate_prologue_modswitch(env, sm.bara, n, pool, pool_stride, job, tid, kTeam);
     env.team_sync();
     {
         const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);

@@ -66,13 +66,7 @@ PEBA1_HD void blind_rotate_wide(Env& env, WideSmem<2 * L>& sm, int team,
     constexpr int kCta = ROWS * kTeam;
     WideTeamSmem& mine = sm.team[team];
 
-    for (int w = ctid; w <= n; w += kCta) {
-        uint32_t t = (w == n) ? (uint32_t)job.c0 : 0u;
-        if (job.in0 >= 0) t += (uint32_t)(int32_t)job.s0 * (uint32_t)env.ldg(pool + (int64_t)job.in0 * pool_stride + w);
-        if (job.in1 >= 0) t += (uint32_t)(int32_t)job.s1 * (uint32_t)env.ldg(pool + (int64_t)job.in1 * pool_stride + w);
-        if (job.in2 >= 0) t += (uint32_t)(int32_t)job.s2 * (uint32_t)env.ldg(pool + (int64_t)job.in2 * pool_stride + w);
-        sm.bara[w] = (uint16_t)((t + (1u << 20)) >> 21);
-    }
+    gate_prologue_modswitch(env, sm.bara, n, pool, pool_stride, job, ctid, kCta);
     env.cta_sync();
     {
         const int rot = (2 * kN - (int)sm.bara[n]) & (2 * kN - 1);
