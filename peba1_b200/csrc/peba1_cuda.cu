@@ -1391,22 +1391,6 @@ int launch_pbs_tm_l(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, cons
         return 0;
     }
 #endif  // PEBA1_ALL_VARIANTS
-#ifdef PEBA1_ALL_VARIANTS
-    if (c->kernel_variant == 12 &&
-        count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * 6)) {
-        // WHAT-IF (timing only until the exchange indices are wired): variant 9 (6 teams, MAC accumulators in registers) with
-        // the cross-team exchange through tensor memory
-        constexpr int T6 = 6;
-        const size_t smem = sizeof(TeamSmemTmX) * (size_t)T6;
-        if (!c->d_job_counter) CU(cudaMalloc(&c->d_job_counter, sizeof(unsigned long long)));
-        CU(cudaMemsetAsync(c->d_job_counter, 0, sizeof(unsigned long long), c->stream));
-        const unsigned grid = std::min((unsigned)((count + T6 - 1) / T6), (unsigned)c->sm_count);
-        auto k = pbs_kernel_tm<L, BGBIT, T6, TeamSmemTmX, true>;
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, T6 * kTeam, smem, c->stream>>>(c->bkfft, c->p.n, pool, stride, jobs, count, u, c->d_job_counter);
-        return 0;
-    }
-#endif
     if (c->kernel_variant == 8 &&
         count >= (c->pair_min_batch >= 0 ? c->pair_min_batch : (int64_t)c->sm_count * kTeamsTm)) {
         // two alternating exchange buffers without the "buffer free" mbarrier (TeamSmemTm2): what the default does for
@@ -2390,7 +2374,7 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
         return 0;
     }
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 12) return fail(PEBA1_EINVAL, "kernel_variant must be 0..12");
+        if (value < 0 || value > 11) return fail(PEBA1_EINVAL, "kernel_variant must be 0..11");
 #ifndef PEBA1_ALL_VARIANTS
         if (value != 1 && value != 8 && value != 11)
             return fail(PEBA1_EINVAL, "kernel_variant %lld lost against the default and is not compiled into this build "
