@@ -122,6 +122,69 @@ def test_errors(engine):
         engine.download(cap, 1)
 
 
+def test_host_buffer_calls_leave_the_pool_alone(engine, keys):
+    """peba1_cuda_gate_batch_host / _keyswitch_host work on private rows: device-resident slots a caller keeps in the pool
+    (the recorder allocates from slot 0) are not clobbered."""
+    rng = np.random.default_rng(5)
+    n = 12
+    resident = keys.encrypt(rng.integers(0, 2, size=4 * n), 61)
+    engine.reserve(4 * n)
+    engine.upload(0, resident)
+    a, b, c = (rng.integers(0, 2, size=n) for _ in range(3))
+    ca, cb, cc = keys.encrypt(a, 62), keys.encrypt(b, 63), keys.encrypt(c, 64)
+    assert np.array_equal(keys.decrypt(engine.gate_batch_host("XOR", ca, cb)), a ^ b)
+    assert np.array_equal(keys.decrypt(engine.gate_batch_host("MUX", ca, cb, cc)), np.where(a == 1, b, c))
+    u = engine.bootstrap_woks_host(ca)
+    assert np.array_equal(engine.keyswitch_host(u), np.stack([keys.keyswitch(row) for row in u]))
+    assert np.array_equal(engine.download(0, 4 * n), resident)
+
+
+def test_in_place_level_larger_than_one_launch_is_refused(engine, keys):
+    """Level semantics hold inside one launch pair; a chunked level whose later chunk reads what an earlier chunk writes
+    would depend on the chunk size: PEBA1_EINVAL instead.  Disjoint chunks run fine."""
+    import peba1_b200 as P
+    from peba1_b200.cuda import make_gates
+    rng = np.random.default_rng(6)
+    n = 10
+    a, b = rng.integers(0, 2, size=n), rng.integers(0, 2, size=n)
+    engine.reserve(3 * n)
+    engine.upload(0, keys.encrypt(a, 71))
+    engine.upload(n, keys.encrypt(b, 72))
+    idx = np.arange(n)
+    engine.set_option("max_pbs_per_launch", 4)
+    try:
+        engine.gates(make_gates("AND", idx, n + idx, 2 * n + idx))                 # 3 chunks, outputs elsewhere
+        assert np.array_equal(keys.decrypt(engine.download(2 * n, n)), a & b)
+        with pytest.raises(P.PEBA1Error, match="in-place levels must fit one launch"):
+            engine.gates(make_gates("AND", idx, n + idx, (idx + 5) % n))            # later chunks read earlier outputs
+        assert np.array_equal(keys.decrypt(engine.download(0, n)), a)              # nothing was launched
+    finally:
+        engine.set_option("max_pbs_per_launch", 0)
+    engine.gates(make_gates("XOR", idx, n + idx, idx))                              # in place within ONE launch: fine
+    assert np.array_equal(keys.decrypt(engine.download(0, n)), a ^ b)
+
+
+def test_level_log_and_device_source_upload(engine, keys):
+    from peba1_b200.cuda import make_gates
+    import torch
+    rng = np.random.default_rng(7)
+    n = 40
+    a, b = rng.integers(0, 2, size=n), rng.integers(0, 2, size=n)
+    words = torch.from_numpy(np.concatenate([keys.encrypt(a, 81), keys.encrypt(b, 82)])).cuda()
+    engine.reserve(3 * n)
+    engine.upload_slots_device(words.data_ptr(), 2 * n, first_slot=0)              # contiguous rows, no host bounce
+    engine.upload_slots_device(words[:n].data_ptr(), n, slots=2 * n + np.arange(n)[::-1])   # scattered
+    engine.sync()
+    assert np.array_equal(keys.decrypt(engine.download(2 * n, n)), a[::-1])
+    idx = np.arange(n)
+    engine.level_log_begin()
+    engine.gates(make_gates("NOR", idx, n + idx, 2 * n + idx))
+    engine.gates(make_gates("MUX", idx[:5], n + idx[:5], 2 * n + idx[:5], in2=idx[:5]))
+    g, p, br, ks = engine.level_log_end()
+    assert g.tolist() == [n, 5] and p.tolist() == [n, 10] and (br > 0).all() and (ks > 0).all()
+    assert np.array_equal(keys.decrypt(engine.download(2 * n + 5, n - 5)), (1 - (a | b))[5:])
+
+
 def test_size_independent_properties_full_batch(engine, keys):
     """BASELINE config 2 size (16,384 gates): properties that need no oracle run.
     NAND(x, x) == NOT x after decryption; XOR(x, y) then XOR(., y) gives x back; all phases within 2^-5 of +-1/8."""
