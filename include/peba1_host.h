@@ -13,7 +13,11 @@
 extern "C" {
 #endif
 
-/* GPU used by contexts created after this call (default: $PEBA1_DEVICE, else $LOCAL_RANK, else 0). */
+/* GPU used by the engines this THREAD creates after the call (and the default of threads that never call it; else
+   $PEBA1_DEVICE, else $LOCAL_RANK, else 0).  Recorder state is per key set (one engine = one GPU context, its own wire
+   table and lock; a ciphertext handle names its engine), so one process can drive several GPUs with one host thread and
+   one key set each; peba1_flush / peba1_batch_begin / _end act on the calling thread's engines only.  A gate whose
+   operands belong to different key sets aborts. */
 void peba1_host_set_device(int device);
 
 /* TEST HOOK — not a fallback.  Engines created after this call hand the four device operations of the recorder to the

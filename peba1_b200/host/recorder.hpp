@@ -18,7 +18,7 @@
 
 namespace peba1 {
 
-using Handle = uint64_t;  // 0: host value (only inside LweSample); else (wire << 1) | neg
+using Handle = uint64_t;  // 0: host value (only inside LweSample); else (engine index + 1) << 40 | (wire << 1) | neg
 constexpr Handle kFalse = 2, kTrue = 3;
 inline bool is_const(Handle h) { return (h >> 1) == 1; }
 inline Handle negate(Handle h) { return h ^ 1; }
@@ -27,7 +27,6 @@ struct Engine;  // one per key material: CUDA context + recorder state
 
 // engine of a cloud key (created on first use; aborts when no device / library error: there is no CPU fallback)
 Engine* engine_of(const TFheGateBootstrappingCloudKeySet* bk);
-Engine* current_engine();  // engine of the most recently used key (for handle release without a key argument)
 
 // reference counting of wires held outside the recorder (samples, circuit-builder temporaries)
 void retain(Handle h);

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <random>
@@ -50,11 +51,16 @@ struct Wire {
     int64_t slot = -1;   // device pool slot while the value is materialised
     int32_t refs = 0;
     int32_t level = 0;   // 0: available (materialised or queued for upload); >0: produced by a pending node
-    int32_t eng = -1;
     int32_t next_free = -1;
 };
 
 struct Engine {
+    // Everything the recorder knows lives in the engine of ONE key set (one GPU context): its wire table, its pending
+    // levels, its statistics, behind its own lock.  Threads that drive different engines (one GPU each) never meet.
+    std::recursive_mutex mu;
+    std::vector<Wire> wires = std::vector<Wire>(2);  // wire 0 unused, wire 1 = constant false
+    int32_t free_wire = -1;
+    peba1_host_stats st{};
     int index = 0;
     peba1_key_material* km = nullptr;
     peba1_cuda_ctx* ctx = nullptr;          // null when a test backend is installed
@@ -69,17 +75,32 @@ struct Engine {
     int routine_depth = 0;
 };
 
-static std::recursive_mutex g_mu;
-static std::vector<Wire> g_wires(2);  // wire 0 unused, wire 1 = constant false
-static int32_t g_free_wire = -1;
+// Process-wide: only the registry of engines (append-only) and the settings.  A handle names its engine in its upper bits
+// ((engine index + 1) << 40 | wire << 1 | negated; the constants 2 and 3 belong to every engine), so samples can be
+// released or fetched without a key argument and without a "current engine".
+static std::recursive_mutex g_mu;        // guards g_engines, the settings below and the process-wide random generator
 static std::vector<Engine*> g_engines;
-static Engine* g_current = nullptr;
-static int g_device = -1;
-static int g_batch_depth = 0;
-static bool g_eager = true;
-static peba1_host_stats g_stats{};
+static int g_device = -1;                // default device of engines created by threads that did not choose one
+static thread_local int t_device = -1;   // peba1_host_set_device is per thread: one host thread per GPU in one process
+static thread_local int t_batch_depth = 0;
+static thread_local std::vector<Engine*> t_engines;  // engines this thread has used (what its flush / batch_end act on)
+static std::atomic<bool> g_eager{true};
+static std::atomic<uint64_t> g_linear{0};  // NOT / COPY / CONSTANT calls (no engine involved)
+constexpr int kEngineShift = 40;
+constexpr Handle kWireMask = (Handle(1) << kEngineShift) - 1;
+static inline int64_t wire_of(Handle h) { return (int64_t)((h & kWireMask) >> 1); }
+static inline Handle mk(const Engine* e, int64_t wire) { return (Handle(e->index + 1) << kEngineShift) | ((Handle)wire << 1); }
+// lock-free lookup (called with an engine lock held): the table is append-only and published by the counter
+constexpr int kMaxEngines = 4096;
+static Engine* g_engine_tab[kMaxEngines];
+static std::atomic<int> g_engine_count{0};
+static Engine* engine_from(Handle h) {
+    const int idx = (int)(h >> kEngineShift);
+    if (idx <= 0 || idx > g_engine_count.load(std::memory_order_acquire)) die("handle %llx names no engine", (unsigned long long)h);
+    return g_engine_tab[idx - 1];
+}
 static const peba1_test_backend* g_test_backend = nullptr;
-static int g_mode = 0;  // peba1_set_mode: 0 faithful, 1 fold + dead-gate elimination, 2 = 1 + MUX-carry adders,
+static std::atomic<int> g_mode{0};  // peba1_set_mode: 0 faithful, 1 fold + dead-gate elimination, 2 = 1 + MUX-carry adders,
                         // 3 = 1 + 3-input full adders (XOR3 / MAJ3) and carry-save column compression (math_circuits.cpp)
 
 // The four engine operations the recorder needs.  The product path is libpeba1_cuda; the table exists only so the
@@ -90,6 +111,7 @@ static int be_download(Engine* e, int64_t slot, int32_t* words);
 static int be_gates(Engine* e, const peba1_gate* gates, int64_t count);
 
 static int pick_device() {
+    if (t_device >= 0) return t_device;
     if (g_device >= 0) return g_device;
     if (const char* s = getenv("PEBA1_DEVICE")) return atoi(s);
     if (const char* s = getenv("LOCAL_RANK")) return atoi(s);
@@ -121,13 +143,16 @@ Engine* engine_of(const TFheGateBootstrappingCloudKeySet* bk) {
                 CUCHK(e, peba1_cuda_load_keyswitch_key(e->ctx, km->ksk.data()));
             }
         }
+        if (e->index >= kMaxEngines) die("more than %d key sets in one process", kMaxEngines);
+        g_engine_tab[e->index] = e;
+        g_engine_count.store(e->index + 1, std::memory_order_release);
         g_engines.push_back(e);
         km->engine = e;
     }
-    g_current = km->engine;
-    return km->engine;
+    Engine* e = km->engine;
+    if (std::find(t_engines.begin(), t_engines.end(), e) == t_engines.end()) t_engines.push_back(e);
+    return e;
 }
-Engine* current_engine() { return g_current; }
 
 static int be_reserve(Engine* e, int64_t slots) {
     return e->tb ? e->tb->reserve(e->tb->user, slots) : peba1_cuda_pool_reserve(e->ctx, slots);
@@ -145,50 +170,50 @@ static int be_gates(Engine* e, const peba1_gate* gates, int64_t count) {
 
 static int64_t new_wire(Engine* e, int level) {
     int64_t id;
-    if (g_free_wire >= 0) {
-        id = g_free_wire;
-        g_free_wire = g_wires[id].next_free;
+    if (e->free_wire >= 0) {
+        id = e->free_wire;
+        e->free_wire = e->wires[id].next_free;
     } else {
-        id = (int64_t)g_wires.size();
-        g_wires.emplace_back();
+        id = (int64_t)e->wires.size();
+        e->wires.emplace_back();
     }
-    Wire& w = g_wires[id];
+    Wire& w = e->wires[id];
     w.slot = -1;
     w.refs = 1;
     w.level = level;
-    w.eng = e->index;
     w.next_free = -1;
     return id;
 }
 
-static void unref_wire(int64_t id) {
-    Wire& w = g_wires[id];
+static void unref_wire(Engine* e, int64_t id) {
+    Wire& w = e->wires[id];
     if (--w.refs > 0) return;
     if (w.refs < 0) die("wire %lld released twice", (long long)id);
-    Engine* e = g_engines[w.eng];
     if (w.slot >= 0) {
         e->free_slots.push_back(w.slot);
-        g_stats.live_slots--;
+        e->st.live_slots--;
     }
     w.slot = -1;
-    w.next_free = g_free_wire;
-    g_free_wire = (int32_t)id;
+    w.next_free = e->free_wire;
+    e->free_wire = (int32_t)id;
 }
 
 void retain(Handle h) {
     if (h == 0 || is_const(h)) return;
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    g_wires[h >> 1].refs++;
+    Engine* e = engine_from(h);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    e->wires[wire_of(h)].refs++;
 }
 void release(Handle h) {
     if (h == 0 || is_const(h)) return;
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    unref_wire((int64_t)(h >> 1));
+    Engine* e = engine_from(h);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    unref_wire(e, wire_of(h));
 }
 
 static int64_t alloc_slot(Engine* e) {
-    g_stats.live_slots++;
-    if (g_stats.live_slots > g_stats.peak_slots) g_stats.peak_slots = g_stats.live_slots;
+    e->st.live_slots++;
+    if (e->st.live_slots > e->st.peak_slots) e->st.peak_slots = e->st.live_slots;
     if (!e->free_slots.empty()) {
         int64_t s = e->free_slots.back();
         e->free_slots.pop_back();
@@ -204,27 +229,29 @@ static void ensure_capacity(Engine* e) {
 }
 
 // fills operand q of a node from a handle; returns the operand's level
-static int set_operand(peba1_gate& g, int q, Handle h) {
+static int set_operand(Engine* e, peba1_gate& g, int q, Handle h) {
     if (h == 0) die("internal: host handle used as a gate operand");
     if (is_const(h)) {
         g.flags |= PEBA1_IN_CONST(q);
         g.in[q] = (int64_t)(h & 1);
         return 0;
     }
-    g.in[q] = (int64_t)(h >> 1);
+    if ((h >> kEngineShift) != (Handle)(e->index + 1))
+        die("a gate mixes ciphertexts of two key sets (operand %d belongs to another engine)", q);
+    g.in[q] = wire_of(h);
     if (h & 1) g.flags |= PEBA1_IN_NEG(q);
-    Wire& w = g_wires[h >> 1];
+    Wire& w = e->wires[wire_of(h)];
     w.refs++;  // the pending node holds its operands
     return w.level;
 }
 
 static Handle push_node(Engine* e, peba1_gate& g, int level) {
     const int64_t out = new_wire(e, level);  // the node's own reference, dropped after execution
-    g_wires[out].refs++;                     // the caller's reference
+    e->wires[out].refs++;                    // the caller's reference
     g.out = out;
     if ((int)e->levels.size() < level) e->levels.resize(level);
     e->levels[level - 1].push_back(g);
-    return (Handle)out << 1;
+    return mk(e, out);
 }
 
 // Boolean function of a 2-input gate (SURVEY.md §8a constants)
@@ -246,9 +273,9 @@ static inline int eval2(int op, int x, int y) {
 static Handle record_gate_raw(Engine* e, int op, Handle a, Handle b) {
     peba1_gate g{};
     g.op = op;
-    const int la = set_operand(g, 0, a), lb = set_operand(g, 1, b);
-    g_stats.gates++;
-    g_stats.pbs++;
+    const int la = set_operand(e, g, 0, a), lb = set_operand(e, g, 1, b);
+    e->st.gates++;
+    e->st.pbs++;
     return push_node(e, g, 1 + std::max(la, lb));
 }
 
@@ -258,7 +285,7 @@ static Handle record_gate_raw(Engine* e, int op, Handle a, Handle b) {
 struct FoldOperand { int64_t var; int neg; int cst; };  // var < 0: constant cst
 static inline FoldOperand fold_operand(Handle h) {
     if (is_const(h)) return FoldOperand{-1, 0, (int)(h & 1)};
-    return FoldOperand{(int64_t)(h >> 1), (int)(h & 1), 0};
+    return FoldOperand{wire_of(h), (int)(h & 1), 0};
 }
 static inline int fold_value(const FoldOperand& o, const int64_t* vars, const int* vals, int nvars) {
     if (o.var < 0) return o.cst;
@@ -289,29 +316,29 @@ static bool try_fold(Engine* e, const Handle* in, int nin, Fn fn, Handle* out) {
         table[m] = fn(v);
     }
     auto alias = [&](int64_t var, int neg) {
-        const Handle h = ((Handle)var << 1) | (Handle)neg;
+        const Handle h = mk(e, var) | (Handle)neg;
         retain(h);
         *out = h;
     };
-    if (nvars == 0) { *out = table[0] ? kTrue : kFalse; g_stats.folded++; return true; }
+    if (nvars == 0) { *out = table[0] ? kTrue : kFalse; e->st.folded++; return true; }
     if (nvars == 1) {
         if (table[0] == table[1]) *out = table[0] ? kTrue : kFalse;
         else alias(vars[0], table[0]);  // table = {0,1}: x ; {1,0}: NOT x
-        g_stats.folded++;
+        e->st.folded++;
         return true;
     }
     // two variables x = vars[0] (bit 0 of m), y = vars[1] (bit 1 of m)
     const bool dep_x = table[0] != table[1] || table[2] != table[3];
     const bool dep_y = table[0] != table[2] || table[1] != table[3];
-    if (!dep_x && !dep_y) { *out = table[0] ? kTrue : kFalse; g_stats.folded++; return true; }
-    if (!dep_y) { alias(vars[0], table[0]); g_stats.folded++; return true; }
-    if (!dep_x) { alias(vars[1], table[0]); g_stats.folded++; return true; }
+    if (!dep_x && !dep_y) { *out = table[0] ? kTrue : kFalse; e->st.folded++; return true; }
+    if (!dep_y) { alias(vars[0], table[0]); e->st.folded++; return true; }
+    if (!dep_x) { alias(vars[1], table[0]); e->st.folded++; return true; }
     for (int op = PEBA1_OP_NAND; op <= PEBA1_OP_ORYN; ++op) {
         bool ok = true;
         for (int m = 0; m < 4 && ok; ++m) ok = eval2(op, m & 1, (m >> 1) & 1) == table[m];
         if (ok) {
-            *out = record_gate_raw(e, op, (Handle)vars[0] << 1, (Handle)vars[1] << 1);
-            g_stats.folded++;
+            *out = record_gate_raw(e, op, mk(e, vars[0]), mk(e, vars[1]));
+            e->st.folded++;
             return true;
         }
     }
@@ -319,7 +346,7 @@ static bool try_fold(Engine* e, const Handle* in, int nin, Fn fn, Handle* out) {
 }
 
 Handle record_gate(Engine* e, int op, Handle a, Handle b) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (g_mode >= 1) {
         const Handle in[2] = {a, b};
         Handle out;
@@ -329,7 +356,7 @@ Handle record_gate(Engine* e, int op, Handle a, Handle b) {
 }
 
 Handle record_mux(Engine* e, Handle sel, Handle if1, Handle if0) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (g_mode >= 1) {
         const Handle in[3] = {sel, if1, if0};
         Handle out;
@@ -337,16 +364,16 @@ Handle record_mux(Engine* e, Handle sel, Handle if1, Handle if0) {
     }
     peba1_gate g{};
     g.op = PEBA1_OP_MUX;
-    const int l0 = set_operand(g, 0, sel), l1 = set_operand(g, 1, if1), l2 = set_operand(g, 2, if0);
-    g_stats.gates++;
-    g_stats.pbs += 2;
+    const int l0 = set_operand(e, g, 0, sel), l1 = set_operand(e, g, 1, if1), l2 = set_operand(e, g, 2, if0);
+    e->st.gates++;
+    e->st.pbs += 2;
     return push_node(e, g, 1 + std::max(l0, std::max(l1, l2)));
 }
 
 // 3-input gates in ONE bootstrap (PEBA1_OP_XOR3 / PEBA1_OP_MAJ3; not part of upstream's API, used by circuit mode 3):
 // sum and carry of a full adder.  Constant, repeated or complementary operands fold like any other gate.
 Handle record_gate3(Engine* e, int op, Handle a, Handle b, Handle c) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     const Handle in[3] = {a, b, c};
     Handle out;
     const bool maj = op == PEBA1_OP_MAJ3;
@@ -354,35 +381,35 @@ Handle record_gate3(Engine* e, int op, Handle a, Handle b, Handle c) {
         return out;
     peba1_gate g{};
     g.op = op;
-    const int l0 = set_operand(g, 0, a), l1 = set_operand(g, 1, b), l2 = set_operand(g, 2, c);
-    g_stats.gates++;
-    g_stats.pbs += 1;
+    const int l0 = set_operand(e, g, 0, a), l1 = set_operand(e, g, 1, b), l2 = set_operand(e, g, 2, c);
+    e->st.gates++;
+    e->st.pbs += 1;
     return push_node(e, g, 1 + std::max(l0, std::max(l1, l2)));
 }
 
 int recorder_mode() { return g_mode; }
 
 Handle wire_from_host(Engine* e, const int32_t* words) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     const int64_t id = new_wire(e, 0);  // reference owned by the upload queue
-    g_wires[id].refs++;                 // the caller's reference
+    e->wires[id].refs++;                // the caller's reference
     e->up_wires.push_back(id);
     e->up_words.insert(e->up_words.end(), words, words + e->words);
-    return (Handle)id << 1;
+    return mk(e, id);
 }
 
 void flush(Engine* e) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (e->up_wires.empty() && e->levels.empty()) return;
     const auto t0 = std::chrono::steady_clock::now();
     // 1. pending uploads
     if (!e->up_wires.empty()) {
         std::vector<int64_t> slots(e->up_wires.size());
-        for (size_t i = 0; i < slots.size(); ++i) slots[i] = g_wires[e->up_wires[i]].slot = alloc_slot(e);
+        for (size_t i = 0; i < slots.size(); ++i) slots[i] = e->wires[e->up_wires[i]].slot = alloc_slot(e);
         ensure_capacity(e);
         CUCHK(e, be_upload_slots(e, slots.data(), (int64_t)slots.size(), e->up_words.data()));
-        g_stats.uploads += slots.size();
-        for (int64_t id : e->up_wires) unref_wire(id);
+        e->st.uploads += slots.size();
+        for (int64_t id : e->up_wires) unref_wire(e, id);
         e->up_wires.clear();
         e->up_words.clear();
     }
@@ -395,12 +422,12 @@ void flush(Engine* e) {
             size_t keep = 0;
             for (size_t i = 0; i < nodes.size(); ++i) {
                 const peba1_gate nd = nodes[i];
-                if (g_wires[nd.out].refs == 1) {
+                if (e->wires[nd.out].refs == 1) {
                     const int nin = nd.op >= PEBA1_OP_MUX ? 3 : 2;
                     for (int q = 0; q < nin; ++q)
-                        if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(nd.in[q]);
-                    unref_wire(nd.out);
-                    g_stats.dead++;
+                        if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(e, nd.in[q]);
+                    unref_wire(e, nd.out);
+                    e->st.dead++;
                 } else {
                     nodes[keep++] = nd;
                 }
@@ -414,55 +441,55 @@ void flush(Engine* e) {
         e->scratch.resize(nodes.size());
         for (size_t i = 0; i < nodes.size(); ++i) {
             const peba1_gate& nd = nodes[i];
-            g_stats.executed_gates++;
-            g_stats.executed_pbs += nd.op == PEBA1_OP_MUX ? 2 : 1;
+            e->st.executed_gates++;
+            e->st.executed_pbs += nd.op == PEBA1_OP_MUX ? 2 : 1;
             peba1_gate& g = e->scratch[i];
             g = nd;
             const int nin = nd.op >= PEBA1_OP_MUX ? 3 : 2;
             for (int q = 0; q < nin; ++q)
-                if (!(nd.flags & PEBA1_IN_CONST(q))) g.in[q] = g_wires[nd.in[q]].slot;
-            g.out = g_wires[nd.out].slot = alloc_slot(e);
+                if (!(nd.flags & PEBA1_IN_CONST(q))) g.in[q] = e->wires[nd.in[q]].slot;
+            g.out = e->wires[nd.out].slot = alloc_slot(e);
         }
         ensure_capacity(e);
         CUCHK(e, be_gates(e, e->scratch.data(), (int64_t)nodes.size()));
-        g_stats.levels++;
-        if (nodes.size() > g_stats.max_level_width) g_stats.max_level_width = nodes.size();
+        e->st.levels++;
+        if (nodes.size() > e->st.max_level_width) e->st.max_level_width = nodes.size();
         for (const peba1_gate& nd : nodes) {
             const int nin = nd.op >= PEBA1_OP_MUX ? 3 : 2;
-            g_wires[nd.out].level = 0;
+            e->wires[nd.out].level = 0;
             for (int q = 0; q < nin; ++q)
-                if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(nd.in[q]);
-            unref_wire(nd.out);
+                if (!(nd.flags & PEBA1_IN_CONST(q))) unref_wire(e, nd.in[q]);
+            unref_wire(e, nd.out);
         }
     }
     e->levels.clear();
-    g_stats.flushes++;
-    g_stats.flush_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    e->st.flushes++;
+    e->st.flush_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 void fetch(Engine* e, Handle h, int32_t* words) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     if (is_const(h)) {
         memset(words, 0, sizeof(int32_t) * (size_t)(e->words - 1));
         words[e->words - 1] = (h & 1) ? (1 << 29) : -(1 << 29);
         return;
     }
-    Wire& w = g_wires[h >> 1];
+    Wire& w = e->wires[wire_of(h)];
     if (w.level > 0 || w.slot < 0) flush(e);
-    if (g_wires[h >> 1].slot < 0) die("internal: wire %llu has no value after a flush", (unsigned long long)(h >> 1));
-    CUCHK(e, be_download(e, g_wires[h >> 1].slot, words));
-    g_stats.downloads++;
+    if (e->wires[wire_of(h)].slot < 0) die("internal: wire %llu has no value after a flush", (unsigned long long)wire_of(h));
+    CUCHK(e, be_download(e, e->wires[wire_of(h)].slot, words));
+    e->st.downloads++;
     if (h & 1)
         for (int i = 0; i < e->words; ++i) words[i] = (int32_t)(0u - (uint32_t)words[i]);
 }
 
 RoutineScope::RoutineScope(const TFheGateBootstrappingCloudKeySet* bk) : e(engine_of(bk)) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     e->routine_depth++;
 }
 RoutineScope::~RoutineScope() {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    if (--e->routine_depth == 0 && g_eager && g_batch_depth == 0) flush(e);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
+    if (--e->routine_depth == 0 && g_eager && t_batch_depth == 0) flush(e);
 }
 
 Handle sample_handle(Engine* e, const LweSample* s) {
@@ -482,7 +509,7 @@ void sample_assign(LweSample* s, Handle h) {
     release(old);
 }
 
-void note_linear() { g_stats.linear++; }
+void note_linear() { g_linear.fetch_add(1, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------------------------------------ randomness
 // One process-wide generator like upstream — but a CSPRNG (ChaCha20, chacha_rng.hpp) keyed from the OS entropy pool at
@@ -683,7 +710,6 @@ TFheGateBootstrappingSecretKeySet* peba1_new_placeholder_keyset(const TFheGateBo
 }
 void delete_gate_bootstrapping_secret_keyset(TFheGateBootstrappingSecretKeySet* keyset) {
     if (!keyset) return;
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
     peba1_key_material* km = keyset->cloud.material;
     // the engine (and the wires of still-allocated ciphertexts) outlives the keyset: main.cpp:600-607 deletes the
     // keyset before the ciphertext arrays.  Pending work is executed, host key copies are dropped.
@@ -737,13 +763,14 @@ void delete_gate_bootstrapping_ciphertext_array(int32_t nbelems, LweSample* samp
 void delete_gate_bootstrapping_ciphertext(LweSample* sample) { delete_gate_bootstrapping_ciphertext_array(1, sample); }
 
 void bootsSymEncrypt(LweSample* result, int32_t message, const TFheGateBootstrappingSecretKeySet* key) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
     const int n = key->params->n;
     std::vector<int32_t> w((size_t)n + 1);
     const uint32_t mu = mod_switch_to_torus32(1, 8);
-    lwe_encrypt(global_rng(), key->lwe_key, n, message ? mu : 0u - mu, key->params->ks_stdev, w.data());
+    {
+        std::lock_guard<std::recursive_mutex> lk(g_mu);  // the process-wide generator only
+        lwe_encrypt(global_rng(), key->lwe_key, n, message ? mu : 0u - mu, key->params->ks_stdev, w.data());
+    }
     peba1_sample_set(result, w.data());
-    (void)n;
 }
 
 int32_t bootsSymDecrypt(const LweSample* sample, const TFheGateBootstrappingSecretKeySet* key) {
@@ -818,14 +845,14 @@ void peba1_encrypt_array_list_device(LweSample* const* arrays, int32_t narrays, 
     if (narrays <= 0 || nbelems <= 0) return;
     if (!arrays || !bits || !key || !key->lwe_key) die("peba1_encrypt_array_list_device: bad arguments");
     Engine* e = engine_of(&key->cloud);
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     const int64_t total = (int64_t)narrays * nbelems;
     std::vector<int64_t> slots((size_t)total);
     for (int32_t k = 0; k < narrays; ++k)
         for (int32_t i = 0; i < nbelems; ++i) {
             const int64_t id = new_wire(e, 0);  // the sample owns the only reference
-            slots[(size_t)k * nbelems + i] = g_wires[id].slot = alloc_slot(e);
-            sample_assign(&arrays[k][i], (Handle)id << 1);
+            slots[(size_t)k * nbelems + i] = e->wires[id].slot = alloc_slot(e);
+            sample_assign(&arrays[k][i], mk(e, id));
         }
     ensure_capacity(e);
     if (e->tb) {
@@ -836,7 +863,7 @@ void peba1_encrypt_array_list_device(LweSample* const* arrays, int32_t narrays, 
         CUCHK(e, peba1_cuda_encrypt_bits(e->ctx, key->lwe_key, bits, slots.data(), 0, total, 0, seed,
                                          key->params->ks_stdev));
     }
-    g_stats.device_encryptions += (uint64_t)total;
+    e->st.device_encryptions += (uint64_t)total;
 }
 // arrays[k][i] <- sample (k*nbelems + i) of a dense DEVICE buffer ((n+1) words each), e.g. what an NCCL broadcast or
 // scatter delivered: the samples become pool-resident wires by one device-side scatter, nothing crosses PCIe.
@@ -846,64 +873,81 @@ void peba1_sample_set_list_device(LweSample* const* arrays, int32_t narrays, int
     if (!arrays || !device_words) die("peba1_sample_set_list_device: bad arguments");
     Engine* e = engine_of(bk);
     if (e->tb) die("peba1_sample_set_list_device needs the CUDA engine (a test backend holds no device memory)");
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     const int64_t total = (int64_t)narrays * nbelems;
     std::vector<int64_t> slots((size_t)total);
     for (int32_t k = 0; k < narrays; ++k)
         for (int32_t i = 0; i < nbelems; ++i) {
             const int64_t id = new_wire(e, 0);  // the sample owns the only reference
-            slots[(size_t)k * nbelems + i] = g_wires[id].slot = alloc_slot(e);
-            sample_assign(&arrays[k][i], (Handle)id << 1);
+            slots[(size_t)k * nbelems + i] = e->wires[id].slot = alloc_slot(e);
+            sample_assign(&arrays[k][i], mk(e, id));
         }
     ensure_capacity(e);
     CUCHK(e, peba1_cuda_upload_slots_device(e->ctx, slots.data(), 0, total, (const int32_t*)device_words));
-    g_stats.uploads += (uint64_t)total;
+    e->st.uploads += (uint64_t)total;
 }
 // the device pool row of a sample that already lives there (-1 otherwise; flushes pending work first): lets a caller
 // gather result ciphertexts on the device, e.g. as the send buffer of an NCCL all-gather
 int64_t peba1_sample_device_slot(const LweSample* sample, const TFheGateBootstrappingCloudKeySet* bk) {
     Engine* e = engine_of(bk);
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::lock_guard<std::recursive_mutex> lk(e->mu);
     const Handle h = sample->peba1_handle;
     if (h == 0 || is_const(h) || (h & 1)) return -1;  // host value, constant, or a negated alias: no row of its own
-    if (g_wires[h >> 1].level > 0 || g_wires[h >> 1].slot < 0) flush(e);
-    return g_wires[h >> 1].slot;
+    if (e->wires[wire_of(h)].level > 0 || e->wires[wire_of(h)].slot < 0) flush(e);
+    return e->wires[wire_of(h)].slot;
 }
 void peba1_encrypt_array_device(LweSample* array, int32_t nbelems, const int32_t* bits,
                                 const TFheGateBootstrappingSecretKeySet* key, uint64_t seed) {
     peba1_encrypt_array_list_device(&array, 1, nbelems, bits, key, seed);
 }
 
-void peba1_host_set_device(int device) { g_device = device; }
+void peba1_host_set_device(int device) {  // this thread's engines; also the default of threads that never call it
+    t_device = device;
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    g_device = device;
+}
 void peba1_host_set_test_backend(const peba1_test_backend* backend) { g_test_backend = backend; }
+static std::vector<Engine*> all_engines() {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    return g_engines;
+}
+// flush / batch scope act on the engines THIS THREAD has used (one host thread per GPU never touches another's)
 void peba1_flush(void) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    for (Engine* e : g_engines) flush(e);
+    for (Engine* e : t_engines) flush(e);
 }
-void peba1_batch_begin(void) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    g_batch_depth++;
-}
+void peba1_batch_begin(void) { t_batch_depth++; }
 void peba1_batch_end(void) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    if (g_batch_depth > 0 && --g_batch_depth == 0) peba1_flush();
+    if (t_batch_depth > 0 && --t_batch_depth == 0) peba1_flush();
 }
 void peba1_set_eager(int eager) { g_eager = eager != 0; }
 void peba1_set_mode(int mode) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    for (Engine* e : g_engines) flush(e);  // pending work was recorded under the old mode
+    for (Engine* e : all_engines()) flush(e);  // pending work was recorded under the old mode
     g_mode = mode < 0 ? 0 : mode > 3 ? 3 : mode;
 }
 int peba1_get_mode(void) { return g_mode; }
-void peba1_get_stats(peba1_host_stats* out) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    if (out) *out = g_stats;
+void peba1_get_stats(peba1_host_stats* out) {  // summed over all engines of the process
+    if (!out) return;
+    peba1_host_stats t{};
+    for (Engine* e : all_engines()) {
+        std::lock_guard<std::recursive_mutex> lk(e->mu);
+        const peba1_host_stats& s = e->st;
+        t.gates += s.gates; t.pbs += s.pbs; t.levels += s.levels; t.flushes += s.flushes;
+        t.max_level_width = std::max(t.max_level_width, s.max_level_width);
+        t.uploads += s.uploads; t.downloads += s.downloads; t.live_slots += s.live_slots; t.peak_slots += s.peak_slots;
+        t.flush_seconds += s.flush_seconds; t.executed_gates += s.executed_gates; t.executed_pbs += s.executed_pbs;
+        t.folded += s.folded; t.dead += s.dead; t.device_encryptions += s.device_encryptions;
+    }
+    t.linear = g_linear.load(std::memory_order_relaxed);
+    *out = t;
 }
 void peba1_reset_stats(void) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
-    const uint64_t live = g_stats.live_slots;
-    g_stats = peba1_host_stats{};
-    g_stats.live_slots = g_stats.peak_slots = live;
+    for (Engine* e : all_engines()) {
+        std::lock_guard<std::recursive_mutex> lk(e->mu);
+        const uint64_t live = e->st.live_slots;
+        e->st = peba1_host_stats{};
+        e->st.live_slots = e->st.peak_slots = live;
+    }
+    g_linear = 0;
 }
 
 int32_t peba1_sample_words(const TFheGateBootstrappingParameterSet* params) { return params->n + 1; }
@@ -932,12 +976,7 @@ void peba1_sample_get_words(const LweSample* sample, int32_t* words) {
         memset(words, 0, sizeof(int32_t) * (size_t)n);
         words[n] = (h & 1) ? (1 << 29) : -(1 << 29);
     } else {
-        Engine* e;
-        {
-            std::lock_guard<std::recursive_mutex> lk(g_mu);
-            e = g_engines[g_wires[h >> 1].eng];
-        }
-        fetch(e, h, words);
+        fetch(engine_from(h), h, words);
     }
 }
 void peba1_sample_set(LweSample* sample, const int32_t* words) {

@@ -553,3 +553,48 @@ def test_out_of_range_sizes_are_refused_not_overrun():
         __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert out.returncode != 0 and "needs 2 * bitsize - 1 samples" in out.stderr
+
+
+def test_two_key_sets_driven_by_two_threads():
+    """One engine per key set, each with its own wire table and lock, handles that name their engine, batch scope per
+    thread: two host threads (one GPU each in production; two simulators here) record and flush concurrently."""
+    import threading
+    L = H.load_library()
+    sims, sets = [], []
+    for seed in (21, 22):
+        sim = SimBackend()
+        sim.install()
+        ks = H.KeySet.generate(128, seed=seed)
+        sim.keyset = ks
+        tmp = ks.new_array(2)                       # the engine is created on first use, while this simulator is installed
+        L.bootsAND(ks.at(tmp, 0), ks.at(tmp, 0), ks.at(tmp, 1), ks.cloud)
+        ks.get_words(tmp, 1)
+        ks.free_array(2, tmp)
+        sims.append(sim); sets.append(ks)
+    L.peba1_host_set_test_backend(None)
+    results, errors = {}, []
+
+    def work(k):
+        try:
+            ks = sets[k]
+            rng = np.random.default_rng(100 + k)
+            out = []
+            for trial in range(6):
+                x, y = (int(v) for v in rng.integers(0, 256, size=2))
+                a, b = ks.encrypt_int(x, 8, 10 * trial + k), ks.encrypt_int(y, 8, 10 * trial + 5 + k)
+                r = ks.new_array(23)
+                L.peba1_batch_begin()               # this thread's scope only
+                L.peba1_math_multiply(r, a, b, 8, 0, ks.cloud)
+                L.peba1_batch_end()
+                out.append((x * y, ks.decrypt_int(r, 23)))
+                for arr, n in ((a, 8), (b, 8), (r, 23)):
+                    ks.free_array(n, arr)
+            results[k] = out
+        except Exception as e:                      # noqa: BLE001
+            errors.append(e)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not errors, errors
+    for k in range(2):
+        assert all(want == got for want, got in results[k]), results[k]
