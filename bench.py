@@ -552,6 +552,9 @@ def main():
         "roofline_keyswitch": {"bound": "l2 (not hbm)", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": ks_ms,
                                "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"), "traffic_source": NCU_SOURCE["keyswitch"],
+                               "l2_ncu": {"lts__throughput_pct": 83.0, "l1tex__throughput_pct": 69.8,
+                                          "l2_to_l1_bytes_per_launch": 6679505950 * 32,
+                                          "source": "profiles/r1s_keyswitch_kernel_ncu.txt (same kernel, batch 16,384): what binds it"},
                                "note": "algorithmic bytes = 62.0 MB key + batch x (4100 in + 2524 out) against MEASURED_PEAKS.json "
                                        "hbm_gbs" + ("" if peaks else " (fallback 6650)") + ": the HBM fraction is tiny by "
                                        "construction — every ciphertext selects its own ~6,144 of the 24,576 key rows, so the key is "
