@@ -34,13 +34,14 @@ sys.path.insert(0, ROOT)
 
 F_PBS = 630 * 258048            # FP64 flops per bootstrap: 162,570,240
 KSK_BYTES = 62029824            # non-zero keyswitch-key rows, unpadded
+KSK_LUT_BYTES = 1024 * 2 * 255 * 2524   # the same key as 255 row sums per group of 4 digits (1.32 GB), what K2 reads
 KEY_SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this very
-# command at batch 16,384 (profiles/r1zz_pbs_kernel_tm_final_ncu.txt, profiles/r1s_keyswitch_kernel_ncu.txt); reported as
+# command at batch 16,384 (profiles/r2a_pbs_kernel_tm_TeamSmemTm2_ncu.txt, profiles/r2p_keyswitch_lut_kernel_ncu.txt); reported as
 # roofline.traffic when the run uses that batch, null otherwise.
-NCU_TRAFFIC = {16384: {"blind_rotate": 573091072 + 68749312, "keyswitch": 402676992 + 43154688}}
+NCU_TRAFFIC = {16384: {"blind_rotate": 573091072 + 68749312, "keyswitch": 11755765000 + 40084480}}
 NCU_SOURCE = {"blind_rotate": "profiles/r2a_pbs_kernel_tm_TeamSmemTm2_ncu.txt (the shipped default instantiation)",
-              "keyswitch": "profiles/r1s_keyswitch_kernel_ncu.txt"}
+              "keyswitch": "profiles/r2p_keyswitch_lut_kernel_ncu.txt"}
 FP64_PEAK_NOMINAL = 148 * 64 * 2 * 1.965e9 / 1e12   # 37.2 TFLOP/s: 148 SMs x 64 DFMA lanes x 2 flop x 1.965 GHz
 
 
@@ -526,7 +527,10 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     achieved_tf = pbs_per_step * F_PBS / (br_ms * 1e-3) / 1e12
-    ks_bytes = KSK_BYTES + B * (4100 + 2524)
+    # keyswitch through the table of row sums (csrc: keyswitch_lut_kernel): 1024 x 2 groups x 255 sums of 2,524 bytes are the
+    # key as the kernel reads it; a ciphertext fetches one row per non-zero group of 4 digits (2,048 x 255/256 of them)
+    ks_bytes = KSK_LUT_BYTES + B * (4100 + 2524)
+    ks_l2_bytes = B * 2048 * (255 / 256) * 2528
     cfg = workload_config(args)
     line = {
         "metric": "bootstrapped gates/s (PBS/s)", "value": value, "unit": "PBS/s", "n_gpus": world,
@@ -549,16 +553,22 @@ def main():
                      "note": "dominant kernel = blind rotation (FP64 vector pipe; neither hbm nor tensor applies). "
                              "achieved = 162,570,240 flop/PBS x PBS per launch / CUDA-event time of the launch; traffic = "
                              "DRAM bytes per launch (the key stays L2-resident)"},
-        "roofline_keyswitch": {"bound": "l2 (not hbm)", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
+        "roofline_keyswitch": {"bound": "l2->sm fabric (not hbm)", "achieved": ks_bytes / (ks_ms * 1e-3) / 1e9, "peak": hbm_peak,
                                "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": ks_ms,
+                               "kernel": "keyswitch_lut_kernel<8,2,4> (one row sum per group of 4 digits)",
                                "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"), "traffic_source": NCU_SOURCE["keyswitch"],
-                               "l2_ncu": {"lts__throughput_pct": 83.0, "l1tex__throughput_pct": 69.8,
-                                          "l2_to_l1_bytes_per_launch": 6679505950 * 32,
-                                          "source": "profiles/r1s_keyswitch_kernel_ncu.txt (same kernel, batch 16,384): what binds it"},
-                               "note": "algorithmic bytes = 62.0 MB key + batch x (4100 in + 2524 out) against MEASURED_PEAKS.json "
-                                       "hbm_gbs" + ("" if peaks else " (fallback 6650)") + ": the HBM fraction is tiny by "
-                                       "construction — every ciphertext selects its own ~6,144 of the 24,576 key rows, so the key is "
-                                       "re-read from L2 per ciphertext tile; the kernel's own bound is the L2/L1 path (DESIGN.md §5 K2)"},
+                               "l2_to_sm": {"row_bytes_per_launch": ks_l2_bytes, "achieved": ks_l2_bytes / (ks_ms * 1e-3) / 1e9,
+                                            "unit": "GB/s", "peak": None,
+                                            "note": "row fetches x 2,528 bytes / kernel time; no independent peak for this path "
+                                                    "(the profiling guide has none) — ncu's lts__throughput below is the evidence"},
+                               "l2_ncu": {"lts__throughput_pct": 73.9, "l1tex__throughput_pct": 69.6, "lts_hit_rate_pct": 71.2,
+                                          "lts_sectors_read": 2048840791, "dram_read_bytes_per_launch": 11755765000,
+                                          "source": "profiles/r2p_keyswitch_lut_kernel_ncu.txt (this kernel, batch 16,384, 4 ciphertexts per CTA)"},
+                               "note": "algorithmic bytes = the key as 1.32 GB of row sums + batch x (4100 in + 2524 out) against "
+                                       "MEASURED_PEAKS.json hbm_gbs" + ("" if peaks else " (fallback 6650)") + ". Every ciphertext "
+                                       "selects its own ~2,040 of the 522,240 rows, so the rows cross the L2->SM fabric once per "
+                                       "ciphertext by construction of the algorithm: that path is the bound (l2_to_sm), HBM only "
+                                       "streams the table once per wave of CTAs (DESIGN.md §5 K2)"},
         "other_ops": other or None,
         "face_match_strong": face_strong,
         "face_match": ({k: v for k, v in face_strong.items() if k != "level_histogram_rank0"} if face_strong else None),

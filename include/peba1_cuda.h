@@ -168,6 +168,12 @@ int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* ctx, double* tflops);
      tm_teams         teams per CTA of the narrow shapes (0 = by batch size)      teams_per_cta   the same for variant 0
      wide_max_batch   batches up to this size use the low-latency kernel (-1 = one bootstrap per SM at most)
      ks_split         CTAs per ciphertext in the keyswitch of narrow levels (-1 = by batch size, 0 = never)
+     ks_lut           digits per row of the keyswitch's table of row sums: 4 (default; 255 sums per group of 4 digits,
+                      1.34 GB of device memory per key, built on the device when first needed), 2 (15 sums, 157 MB) or
+                      0 (no table: one key row per non-zero digit, as TFHE does it).  Same output words either way.
+     ks_lut_group     ciphertexts per CTA of that kernel (1 or 4) on levels at least ks_lut_group_min wide
+                      (-1, default: eight waves of single-ciphertext CTAs, 14,208 on 148 SMs)
+     ks_lut_min       levels narrower than this use the per-digit kernels (default 1)
      narrow_two_buffers  1: the narrow shapes use the two-buffer layout of the wide-batch kernel too (default 0)
      ks_group, pair_min_batch, tmk_stagger_ns, max_pbs_per_launch: see peba1_cuda.cu */
 int peba1_cuda_set_option(peba1_cuda_ctx* ctx, const char* name, int64_t value);

@@ -999,6 +999,120 @@ __global__ void __launch_bounds__(kKsThreads)
         if (w0 + q <= n) atomicAdd(out + w0 + q, r[q]);
 }
 
+// K2 for wide levels through a table of ROW SUMS.  The M digits of a group (M = 2, 4) select M key rows whose sum is
+// subtracted; the table holds that sum for every combined digit value D = 1 .. 4^M - 1, so one row fetch replaces up to
+// M (on average 3M/4) — 2,040 instead of 6,144 rows of 2.5 KB per ciphertext at M = 4, and the L2 -> SM fabric
+// (64 B/clk per SM) that binds the per-digit kernel carries a third of the bytes.  The same rows of the same key are
+// added in another order, and addition mod 2^32 is associative: the output words are identical.  Cost: (4^M - 1)/(3M)
+// times the key in HBM (1.34 GB at M = 4, built on the device when a wide level first needs it).  The CTAs of a launch
+// walk the coefficients together, so the part of the table in use at any time (1.3 MB per coefficient) stays in L2.
+// Layout: [i][g][D-1][stride], g = group of digits gM .. gM+M-1, the first digit in the top bits of D.
+template <int T, int BASEBIT, int M>
+__global__ void ksk_lut_build_kernel(const int32_t* __restrict__ ksk, int64_t kstride, int32_t* __restrict__ lut) {
+    constexpr int BASE = 1 << BASEBIT, NG = T / M, ROWS = (1 << (BASEBIT * M)) - 1;
+    const int64_t r = blockIdx.x;  // output row
+    const int D = (int)(r % ROWS) + 1;
+    const int64_t ig = r / ROWS;
+    const int g = (int)(ig % NG);
+    const int64_t i = ig / NG;
+    const int32_t* src[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int d = (D >> (BASEBIT * (M - 1 - m))) & (BASE - 1);
+        src[m] = d ? ksk + ((i * T + g * M + m) * (BASE - 1) + d - 1) * kstride : nullptr;
+    }
+    for (int w = threadIdx.x; w < kstride; w += blockDim.x) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+            if (src[m]) s += (uint32_t)src[m][w];
+        lut[r * kstride + w] = (int32_t)s;
+    }
+}
+
+// G ciphertexts per CTA walk the coefficients together (thread t keeps words 4t..4t+3 of all G): a wide level then has
+// G times fewer waves of CTAs, and each wave streams the table from HBM once.
+template <int T, int BASEBIT, int M, bool SPLIT, int G, int U = 4>
+__global__ void __launch_bounds__(kKsThreads)
+    keyswitch_lut_kernel(const int32_t* __restrict__ lut, int n, int64_t kstride, int64_t stride,
+                         const int32_t* __restrict__ u, const KsJob* __restrict__ jobs, int64_t count, int parts,
+                         int32_t* __restrict__ pool) {
+    static_assert(!SPLIT || G == 1, "a split ciphertext has a CTA range to itself");
+    constexpr int NG = T / M, FIELD = BASEBIT * M;
+    constexpr uint32_t ROWS = (1u << FIELD) - 1;
+    constexpr uint32_t PREC_OFFSET = 1u << (32 - (1 + BASEBIT * T));
+    __shared__ __align__(16) uint32_t abar[kN][G];  // [i][g]: the G words of a coefficient are one broadcast load
+    const int t = threadIdx.x;
+    // SPLIT (narrow levels): the coefficients of a ciphertext are split over `parts` CTAs, partial sums by
+    // red.global.add onto what ks_init_kernel wrote — as in keyswitch_split_kernel
+    const int64_t g0 = SPLIT ? blockIdx.x / parts : (int64_t)blockIdx.x * G;
+    const int part = SPLIT ? blockIdx.x % parts : 0, span = SPLIT ? kN / parts : kN, i0 = part * span;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g0 + g < count) {
+            const KsJob job = jobs[g0 + g];
+            const int32_t* u0 = u + (int64_t)job.u0 * kUStride;
+            const int32_t* u1 = job.u1 >= 0 ? u + (int64_t)job.u1 * kUStride : nullptr;
+            for (int i = t; i < span; i += kKsThreads) {
+                uint32_t a = (uint32_t)u0[i0 + i];
+                if (u1) a += (uint32_t)u1[i0 + i];
+                abar[i][g] = a + PREC_OFFSET;
+            }
+        } else {
+            for (int i = t; i < span; i += kKsThreads) abar[i][g] = 0;  // beyond the batch: every group reads D = 0, nothing is fetched
+        }
+    }
+    __syncthreads();
+    const int w0 = 4 * t;
+    if (w0 > n) return;
+    uint4 acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = make_uint4(0, 0, 0, 0);
+    const uint32_t row_bytes = (uint32_t)kstride * 4u;
+    uint64_t p0 = reinterpret_cast<uint64_t>(lut) + 16u * (uint32_t)t;
+    asm volatile("" : "+l"(p0));
+#pragma unroll(U)
+    for (int i = 0; i < span; ++i) {
+        uint32_t a[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) a[g] = abar[i][g];
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint32_t D = (a[g] >> (32 - (q + 1) * FIELD)) & ROWS;
+                if (D != 0) {
+                    const uint32_t idx = ((uint32_t)(i0 + i) * NG + q) * ROWS + D - 1;
+                    uint64_t addr;
+                    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(row_bytes), "l"(p0));
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(addr));
+                    acc[g].x -= v.x; acc[g].y -= v.y; acc[g].z -= v.z; acc[g].w -= v.w;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g0 + g >= count) break;
+        const KsJob job = jobs[g0 + g];
+        uint32_t r[4] = {acc[g].x, acc[g].y, acc[g].z, acc[g].w};
+        int32_t* out = pool + job.out_slot * stride;
+        if (!SPLIT) {
+            uint32_t bsum = (uint32_t)u[(int64_t)job.u0 * kUStride + kN] + (uint32_t)job.c0;  // b' (+ b'' + c0) goes to word n
+            if (job.u1 >= 0) bsum += (uint32_t)u[(int64_t)job.u1 * kUStride + kN];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (w0 + q == n) r[q] += bsum;
+                if (w0 + q <= n) out[w0 + q] = (int32_t)r[q];
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (w0 + q <= n) atomicAdd(reinterpret_cast<unsigned int*>(out) + w0 + q, r[q]);
+        }
+    }
+}
+
 // K2 for wide levels, TILED: the key is streamed once per TILE of ciphertexts instead of once per ciphertext.
 // The one-CTA-per-ciphertext kernel above pulls ~6,144 rows of 2.5 KB per ciphertext through the L1 data pipe: 214 GB of
 // L2->SM traffic per 16,384 ciphertexts (ncu r1s: lts 83 %, L1 70 % busy) for 62 MB of key.  Here a thread keeps 8 output
@@ -1206,6 +1320,10 @@ struct peba1_cuda_ctx {
     int32_t* pool = nullptr;
     int64_t pool_slots = 0, pool_stride = 0;
     int64_t ksk_stride = 0;  // words per packed keyswitch-key row
+    // table of row sums for the keyswitch of wide levels (keyswitch_lut_kernel): built on first use, dropped when the key changes
+    int32_t* ksk_lut = nullptr;
+    int ksk_lut_digits = 0;  // digits per group the table was built for (0 = not built)
+    int ksk_lut_alloc = 0;   // digits per group the buffer is sized for
     // workspaces (grown on demand)
     int32_t* u = nullptr;
     int64_t u_cap = 0;  // in samples
@@ -1241,6 +1359,10 @@ struct peba1_cuda_ctx {
     int ks_tile = 0;         // ciphertexts per group of the tiled keyswitch (8, 12, 16; 0 = off), 2 groups per CTA
     int ks_tile_parts = 1;   // CTAs per tile (coefficient ranges, partial sums by red.global.add)
     int64_t ks_tile_min = 4096;  // levels narrower than this keep the per-ciphertext kernels
+    int ks_lut = 4;          // digits per table row of the wide-level keyswitch (4: 255 row sums per group, 1.34 GB; 2: 15, 157 MB; 0 = off)
+    int ks_lut_group = 4;    // ciphertexts per CTA of that kernel on very wide levels (1 or 4)
+    int64_t ks_lut_group_min = -1;  // ... from this level width on; -1 = eight waves of single-ciphertext CTAs (14,208 on 148 SMs)
+    int64_t ks_lut_min = 1;  // levels narrower than this keep the per-digit kernels (a context that stays below it never builds the table)
     int64_t ks_split = -1;   // CTAs per ciphertext in the keyswitch of a narrow level: -1 by batch size, 0 never, else fixed (power of 2)
     int kernel_variant = 1;  // see include/peba1_cuda.h (peba1_cuda_set_option): 1 is the product, 0 and 2..10 are the
                              // measured alternatives
@@ -1549,6 +1671,29 @@ int launch_pbs(peba1_cuda_ctx* c, const int32_t* pool, int64_t stride, const Pbs
 #endif
 }
 
+// the table of row sums for c->ks_lut digits per group, built from the packed key on the context's stream
+int ensure_ksk_lut(peba1_cuda_ctx* c) {
+    if (c->ksk_lut_digits == c->ks_lut) return 0;
+    const int M = c->ks_lut;
+    const int64_t rows = (int64_t)kN * (c->p.ks_t / M) * ((1 << (c->p.ks_basebit * M)) - 1);
+    c->ksk_lut_digits = 0;
+    if (c->ksk_lut && c->ksk_lut_alloc != M) {  // another table shape: launches that read the old one are on this stream
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(c->ksk_lut));
+        c->ksk_lut = nullptr;
+    }
+    if (!c->ksk_lut) {
+        CU(cudaMalloc(&c->ksk_lut, (size_t)rows * c->ksk_stride * sizeof(int32_t)));
+        c->ksk_lut_alloc = M;
+    }
+    if (M == 2) ksk_lut_build_kernel<8, 2, 2><<<(unsigned)rows, 160, 0, c->stream>>>(c->ksk, c->ksk_stride, c->ksk_lut);
+    else ksk_lut_build_kernel<8, 2, 4><<<(unsigned)rows, 160, 0, c->stream>>>(c->ksk, c->ksk_stride, c->ksk_lut);
+    CU(cudaGetLastError());
+    c->stats.launches++;
+    c->ksk_lut_digits = M;
+    return 0;
+}
+
 int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t count, int32_t* pool) {
     if (count <= 0) return 0;
     const int G = c->ks_group;
@@ -1558,6 +1703,28 @@ int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t co
         const int64_t room = (int64_t)c->sm_count * 12 / std::max<int64_t>(count, 1);
         while (parts * 2 <= room && parts < 16) parts *= 2;
         if (c->ks_split > 0) parts = (int)c->ks_split;
+    }
+    // one fetch per group of digits from the table of row sums (any width; narrow levels split as above)
+    if (G == 1 && c->ks_lut > 0 && c->ks_tile == 0 && count >= c->ks_lut_min) {
+        if (int rc = ensure_ksk_lut(c)) return rc;
+        if (parts > 1) ks_init_kernel<<<(unsigned)count, 160, 0, c->stream>>>(c->p.n, c->pool_stride, u, jobs, count, pool);
+        // several ciphertexts per CTA once the level is wider than one wave of single-ciphertext CTAs
+        const int64_t group_from = c->ks_lut_group_min >= 0 ? c->ks_lut_group_min : (int64_t)c->sm_count * 12 * 8;
+        const int LG = (parts == 1 && c->ks_lut == 4 && count >= group_from) ? c->ks_lut_group : 1;
+        const unsigned lgrid = parts > 1 ? (unsigned)(count * parts) : (unsigned)((count + LG - 1) / LG);
+#define PEBA1_KS_LUT(M, SPLIT, GRP, UNR) keyswitch_lut_kernel<8, 2, M, SPLIT, GRP, UNR><<<lgrid, kKsThreads, 0, c->stream>>>( \
+    c->ksk_lut, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, parts, pool)
+        // unroll depths by measurement (profiles/r2p_keyswitch_lut_kbench.log): loads in flight per thread are what counts
+        if (parts > 1) { if (c->ks_lut == 2) PEBA1_KS_LUT(2, true, 1, 4); else PEBA1_KS_LUT(4, true, 1, 4); }
+        else if (c->ks_lut == 2) PEBA1_KS_LUT(2, false, 1, 4);
+        else if (LG == 4) PEBA1_KS_LUT(4, false, 4, 2);
+        else PEBA1_KS_LUT(4, false, 1, 8);
+#undef PEBA1_KS_LUT
+        CU(cudaGetLastError());
+        if (c->timing) CU(cudaEventRecord(c->ev2, c->stream));
+        c->stats.launches += parts > 1 ? 2 : 1;
+        c->stats.keyswitches += (uint64_t)count;
+        return 0;
     }
     if (parts > 1) {
         ks_init_kernel<<<(unsigned)count, 160, 0, c->stream>>>(c->p.n, c->pool_stride, u, jobs, count, pool);
@@ -1714,7 +1881,7 @@ int peba1_cuda_destroy(peba1_cuda_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->bkfft); cudaFree(c->ksk); cudaFree(c->pool); cudaFree(c->u); cudaFree(c->d_jobs); cudaFree(c->d_job_counter); cudaFree(c->d_stage);
+    cudaFree(c->bkfft); cudaFree(c->ksk); cudaFree(c->ksk_lut); cudaFree(c->pool); cudaFree(c->u); cudaFree(c->d_jobs); cudaFree(c->d_job_counter); cudaFree(c->d_stage);
     cudaFree(c->hb_pool);
     for (cudaEvent_t e : c->log_ev) cudaEventDestroy(e);
     if (c->stream_switch) cudaEventDestroy(c->stream_switch);
@@ -1784,6 +1951,7 @@ int peba1_cuda_load_keyswitch_key(peba1_cuda_ctx* c, const int32_t* ksk_host) {
     c->stats.launches++;
     CU(cudaStreamSynchronize(c->stream));
     c->ksk_loaded = true;
+    c->ksk_lut_digits = 0;  // the row sums belong to the previous key
     return 0;
 }
 
@@ -1799,6 +1967,7 @@ int peba1_cuda_key_device_buffers(peba1_cuda_ctx* c, void** bkfft, uint64_t* bkf
 int peba1_cuda_keys_mark_loaded(peba1_cuda_ctx* c) {
     if (!c) return fail(PEBA1_EINVAL, "null context");
     c->bk_loaded = c->ksk_loaded = true;
+    c->ksk_lut_digits = 0;  // the caller wrote a key into the device buffers: row sums are rebuilt on next use
     return 0;
 }
 
@@ -2353,6 +2522,25 @@ int peba1_cuda_set_option(peba1_cuda_ctx* c, const char* name, int64_t value) {
     }
     if (!strcmp(name, "ks_tile_min")) {
         c->ks_tile_min = value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_lut")) {
+        if (value != 0 && value != 2 && value != 4) return fail(PEBA1_EINVAL, "ks_lut must be 0 (off), 2 or 4 digits per table row");
+        c->ks_lut = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_lut_group")) {
+        if (value != 1 && value != 4) return fail(PEBA1_EINVAL, "ks_lut_group must be 1 or 4");
+        c->ks_lut_group = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_lut_group_min")) {
+        c->ks_lut_group_min = value;
+        return 0;
+    }
+    if (!strcmp(name, "ks_lut_min")) {
+        if (value < 1) return fail(PEBA1_EINVAL, "ks_lut_min must be at least 1");
+        c->ks_lut_min = value;
         return 0;
     }
     if (!strcmp(name, "ks_split")) {

@@ -264,7 +264,24 @@ def test_kernel_variants_agree(engine, keys):
         engine.set_option("ks_split", 4)         # narrow-level keyswitch split over 4 CTAs per ciphertext
         assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), "ks_split"
         engine.set_option("ks_split", -1)
+        # the keyswitch through a table of row sums (default: 4 digits per row) against one row per digit (0) and the
+        # 2-digit table; whole ciphertexts per CTA (ks_split 0), several of them per CTA (the batch is not a multiple)
+        for lut in (0, 2, 4):
+            engine.set_option("ks_lut", lut)
+            for split in (-1, 0, 8):
+                engine.set_option("ks_split", split)
+                assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), ("ks_lut", lut, split)
+        engine.set_option("ks_split", 0)
+        engine.set_option("ks_lut_group_min", 1)
+        for grp in (4, 1):
+            engine.set_option("ks_lut_group", grp)
+            assert np.array_equal(engine.gate_batch_host("ANDYN", ca, cb), want), ("ks_lut_group", grp)
+            assert np.array_equal(engine.gate_batch_host("ANDYN", ca[:3], cb[:3]), want[:3]), ("ks_lut_group", grp, 3)
     finally:
+        engine.set_option("ks_lut", 4)
+        engine.set_option("ks_lut_group", 4)
+        engine.set_option("ks_lut_group_min", -1)
+        engine.set_option("ks_split", -1)
         engine.set_option("kernel_variant", 1)
         engine.set_option("tm_teams", 0)
         engine.set_option("ks_group", 1)
