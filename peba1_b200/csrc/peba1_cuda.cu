@@ -1683,7 +1683,17 @@ int ensure_ksk_lut(peba1_cuda_ctx* c) {
         c->ksk_lut = nullptr;
     }
     if (!c->ksk_lut) {
-        CU(cudaMalloc(&c->ksk_lut, (size_t)rows * c->ksk_stride * sizeof(int32_t)));
+        const cudaError_t e = cudaMalloc(&c->ksk_lut, (size_t)rows * c->ksk_stride * sizeof(int32_t));
+        if (e == cudaErrorMemoryAllocation) {
+            // no room for the table on this device: this context keeps the per-digit kernels (same words, 3 x the rows)
+            cudaGetLastError();
+            c->ksk_lut = nullptr;
+            fprintf(stderr, "peba1_cuda: %.2f GB for the keyswitch table of row sums not available; using the per-digit keyswitch\n",
+                    (double)rows * c->ksk_stride * sizeof(int32_t) / 1e9);
+            c->ks_lut = 0;
+            return 0;
+        }
+        CU(e);
         c->ksk_lut_alloc = M;
     }
     if (M == 2) ksk_lut_build_kernel<8, 2, 2><<<(unsigned)rows, 160, 0, c->stream>>>(c->ksk, c->ksk_stride, c->ksk_lut);
@@ -1707,6 +1717,8 @@ int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t co
     // one fetch per group of digits from the table of row sums (any width; narrow levels split as above)
     if (G == 1 && c->ks_lut > 0 && c->ks_tile == 0 && count >= c->ks_lut_min) {
         if (int rc = ensure_ksk_lut(c)) return rc;
+    }
+    if (G == 1 && c->ks_lut > 0 && c->ks_tile == 0 && count >= c->ks_lut_min) {  // (the table may just have been refused)
         if (parts > 1) ks_init_kernel<<<(unsigned)count, 160, 0, c->stream>>>(c->p.n, c->pool_stride, u, jobs, count, pool);
         // several ciphertexts per CTA once the level is wider than one wave of single-ciphertext CTAs
         const int64_t group_from = c->ks_lut_group_min >= 0 ? c->ks_lut_group_min : (int64_t)c->sm_count * 12 * 8;
