@@ -11,7 +11,7 @@
 //                                rows in parallel, key rows by TMA (blind_rotate_wide.cuh)
 //            pbs_kernel, pbs_kernel_tmsh, pbs_kernel_pair, pbs_kernel_tmk: measured alternatives (kernel_variant 0, 2, 3, 4)
 //   K2     keyswitch_kernel (one CTA per ciphertext) / ks_init_kernel + keyswitch_split_kernel (narrow levels: a
-//          ciphertext split over up to 16 CTAs): lweKeySwitch over the extracted samples, writes the ciphertext pool
+//          ciphertext split over up to 64 CTAs): lweKeySwitch over the extracted samples, writes the ciphertext pool
 //   K3     key_transform_kernel  bootstrapping key -> transform domain, once per key
 //   K4     linear_kernel         bootsNOT / bootsCOPY / bootsCONSTANT on pool slots
 //          lwe_encrypt_kernel    device-side encryption for synthetic inputs (peba1_cuda_encrypt_bits)
@@ -1707,11 +1707,11 @@ int ensure_ksk_lut(peba1_cuda_ctx* c) {
 int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t count, int32_t* pool) {
     if (count <= 0) return 0;
     const int G = c->ks_group;
-    // narrow level: one wave of CTAs, each ciphertext split over up to 16 of them
+    // narrow level: one wave of CTAs, each ciphertext split over up to 64 of them
     int parts = 1;
     if (G == 1 && c->ks_split != 0) {
         const int64_t room = (int64_t)c->sm_count * 12 / std::max<int64_t>(count, 1);
-        while (parts * 2 <= room && parts < 16) parts *= 2;
+        while (parts * 2 <= room && parts < 64) parts *= 2;
         if (c->ks_split > 0) parts = (int)c->ks_split;
     }
     // one fetch per group of digits from the table of row sums (any width; narrow levels split as above)
@@ -1727,7 +1727,7 @@ int launch_ks(peba1_cuda_ctx* c, const int32_t* u, const KsJob* jobs, int64_t co
 #define PEBA1_KS_LUT(M, SPLIT, GRP, UNR) keyswitch_lut_kernel<8, 2, M, SPLIT, GRP, UNR><<<lgrid, kKsThreads, 0, c->stream>>>( \
     c->ksk_lut, c->p.n, c->ksk_stride, c->pool_stride, u, jobs, count, parts, pool)
         // unroll depths by measurement (profiles/r2p_keyswitch_lut_kbench.log): loads in flight per thread are what counts
-        if (parts > 1) { if (c->ks_lut == 2) PEBA1_KS_LUT(2, true, 1, 4); else PEBA1_KS_LUT(4, true, 1, 4); }
+        if (parts > 1) { if (c->ks_lut == 2) PEBA1_KS_LUT(2, true, 1, 4); else PEBA1_KS_LUT(4, true, 1, 8); }
         else if (c->ks_lut == 2) PEBA1_KS_LUT(2, false, 1, 4);
         else if (LG == 4) PEBA1_KS_LUT(4, false, 4, 2);
         else PEBA1_KS_LUT(4, false, 1, 8);
