@@ -111,6 +111,35 @@ def keyswitch(u, ksk, t_digits=8, basebit=2):
     return out
 
 
+def keyswitch_row_sums(u, ksk, group=4, t_digits=8, basebit=2):
+    """step 6 as the CUDA keyswitch evaluates it (csrc/peba1_cuda.cu: ksk_lut_build_kernel + keyswitch_lut_kernel): the
+    `group` digits of a field select `group` key rows; their SUM is a table entry T[i][g][D], D = the field with the first
+    digit in its top bits, and one entry per non-zero field is subtracted.  Integer addition mod 2^32 is associative, so
+    this returns the words of keyswitch() above — the test says so on the golden chain."""
+    N = len(u) - 1
+    base = 1 << basebit
+    out = np.zeros(ksk.shape[-1], dtype=np.int64)
+    out[-1] = u[N]
+    prec = 1 << (32 - (1 + basebit * t_digits))
+    field = basebit * group
+
+    def entry(i, g, D):  # what ksk_lut_build_kernel stores in row ((i * (t/group) + g) * (4^group - 1) + D - 1)
+        s = np.zeros(ksk.shape[-1], dtype=np.int64)
+        for m in range(group):
+            d = (D >> (basebit * (group - 1 - m))) & (base - 1)
+            if d:
+                s = (s + u32(ksk[i, g * group + m, d])) & M32
+        return s
+
+    for i in range(N):
+        a = (int(u[i]) + prec) & M32
+        for g in range(t_digits // group):
+            D = (a >> (32 - (g + 1) * field)) & ((1 << field) - 1)
+            if D:
+                out = (out - entry(i, g, D)) & M32
+    return out
+
+
 def gate(op, ca, cb, bk, ksk, l=3, Bgbit=7):
     return keyswitch(bootstrap_woks(prologue(op, ca, cb), bk, l, Bgbit), ksk)
 

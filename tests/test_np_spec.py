@@ -44,6 +44,15 @@ def test_golden_bootstrap_and_keyswitch_recomputed_independently(keys):
     assert np.array_equal(S.as_i32(S.prologue("NAND", g["ca"][3], g["cb"][3])), g["pbs_in"])
 
 
+def test_keyswitch_through_row_sums_returns_the_same_words(keys):
+    """the table of key-row sums the CUDA keyswitch reads (one entry per group of 4 or 2 digits) is the per-digit
+    keyswitch in another order of additions: same words on the golden extracted sample"""
+    g = np.load(GOLDEN)
+    u = S.u32(g["pbs_out"])
+    for group in (4, 2):
+        assert np.array_equal(S.as_i32(S.keyswitch_row_sums(u, keys.ksk, group)), g["ks_out"]), group
+
+
 def test_golden_mux_gate_recomputed_independently(keys):
     """one whole bootsMUX (two bootstraps, sum, keyswitch) of the golden set (~30 s)"""
     g = np.load(GOLDEN)
