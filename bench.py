@@ -557,6 +557,10 @@ def main():
                                "unit": "GB/s", "frac": ks_bytes / (ks_ms * 1e-3) / 1e9 / hbm_peak, "kernel_ms": ks_ms,
                                "kernel": "keyswitch_lut_kernel<8,2,4> (one row sum per group of 4 digits)",
                                "traffic": NCU_TRAFFIC.get(B, {}).get("keyswitch"), "traffic_source": NCU_SOURCE["keyswitch"],
+                               # what HBM actually delivers during the launch: ncu's DRAM bytes over this run's kernel time
+                               "hbm_from_traffic": ({"achieved": NCU_TRAFFIC[B]["keyswitch"] / (ks_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                                     "frac": NCU_TRAFFIC[B]["keyswitch"] / (ks_ms * 1e-3) / 1e9 / hbm_peak}
+                                                    if B in NCU_TRAFFIC else None),
                                "l2_to_sm": {"row_bytes_per_launch": ks_l2_bytes, "achieved": ks_l2_bytes / (ks_ms * 1e-3) / 1e9,
                                             "unit": "GB/s", "peak": None,
                                             "note": "row fetches x 2,528 bytes / kernel time; no independent peak for this path "
