@@ -999,13 +999,14 @@ __global__ void __launch_bounds__(kKsThreads)
         if (w0 + q <= n) atomicAdd(out + w0 + q, r[q]);
 }
 
-// K2 for wide levels through a table of ROW SUMS.  The M digits of a group (M = 2, 4) select M key rows whose sum is
-// subtracted; the table holds that sum for every combined digit value D = 1 .. 4^M - 1, so one row fetch replaces up to
-// M (on average 3M/4) — 2,040 instead of 6,144 rows of 2.5 KB per ciphertext at M = 4, and the L2 -> SM fabric
-// (64 B/clk per SM) that binds the per-digit kernel carries a third of the bytes.  The same rows of the same key are
+// K2 through a table of ROW SUMS (the default keyswitch, every level width).  The M digits of a group (M = 2, 4) select M
+// key rows whose sum is subtracted; the table holds that sum for every combined digit value D = 1 .. 4^M - 1, so one row
+// fetch replaces up to M (on average 3M/4): 2,040 instead of 6,144 rows of 2.5 KB per ciphertext at M = 4, a third of the
+// bytes through the L2 -> SM path that binds the per-digit kernel (ncu r1s: lts 83 %).  The same rows of the same key are
 // added in another order, and addition mod 2^32 is associative: the output words are identical.  Cost: (4^M - 1)/(3M)
-// times the key in HBM (1.34 GB at M = 4, built on the device when a wide level first needs it).  The CTAs of a launch
-// walk the coefficients together, so the part of the table in use at any time (1.3 MB per coefficient) stays in L2.
+// times the key in HBM (1.34 GB at M = 4, built on the device when a keyswitch first needs it).  The CTAs of a launch
+// start together and take the same time, so they walk the coefficients in step and the part of the table in use
+// (1.3 MB per coefficient) stays in L2 (ncu r2p: hit rate 71 %, DRAM 11.8 GB per 16,384).
 // Layout: [i][g][D-1][stride], g = group of digits gM .. gM+M-1, the first digit in the top bits of D.
 template <int T, int BASEBIT, int M>
 __global__ void ksk_lut_build_kernel(const int32_t* __restrict__ ksk, int64_t kstride, int32_t* __restrict__ lut) {
@@ -1031,7 +1032,8 @@ __global__ void ksk_lut_build_kernel(const int32_t* __restrict__ ksk, int64_t ks
 }
 
 // G ciphertexts per CTA walk the coefficients together (thread t keeps words 4t..4t+3 of all G): a wide level then has
-// G times fewer waves of CTAs, and each wave streams the table from HBM once.
+// G times fewer waves of CTAs, and each wave streams the table from HBM once.  U = coefficients per unrolled iteration:
+// the loads a thread has in flight (U x T/M x G) decide the speed (profiles/r2p_keyswitch_lut_kbench.log).
 template <int T, int BASEBIT, int M, bool SPLIT, int G, int U = 4>
 __global__ void __launch_bounds__(kKsThreads)
     keyswitch_lut_kernel(const int32_t* __restrict__ lut, int n, int64_t kstride, int64_t stride,
