@@ -10,8 +10,10 @@
 //            pbs_kernel_wide     the latency kernel for at most one bootstrap per SM: one CTA of 2l teams per bootstrap,
 //                                rows in parallel, key rows by TMA (blind_rotate_wide.cuh)
 //            pbs_kernel, pbs_kernel_tmsh, pbs_kernel_pair, pbs_kernel_tmk: measured alternatives (kernel_variant 0, 2, 3, 4)
-//   K2     keyswitch_kernel (one CTA per ciphertext) / ks_init_kernel + keyswitch_split_kernel (narrow levels: a
-//          ciphertext split over up to 64 CTAs): lweKeySwitch over the extracted samples, writes the ciphertext pool
+//   K2     keyswitch_lut_kernel  lweKeySwitch over the extracted samples through a device-built table of key-row sums
+//                                (ksk_lut_build_kernel: one fetch per group of 4 digits), writes the ciphertext pool;
+//                                narrow levels: ks_init_kernel + the same kernel with a ciphertext split over up to 64 CTAs
+//          keyswitch_kernel / keyswitch_split_kernel: one key row per non-zero digit (ks_lut = 0), the form it replaced
 //   K3     key_transform_kernel  bootstrapping key -> transform domain, once per key
 //   K4     linear_kernel         bootsNOT / bootsCOPY / bootsCONSTANT on pool slots
 //          lwe_encrypt_kernel    device-side encryption for synthetic inputs (peba1_cuda_encrypt_bits)
