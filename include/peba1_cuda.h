@@ -175,7 +175,9 @@ int peba1_cuda_measure_fp64_peak(peba1_cuda_ctx* ctx, double* tflops);
                       (-1, default: eight waves of single-ciphertext CTAs, 14,208 on 148 SMs)
      ks_lut_min       levels narrower than this use the per-digit kernels (default 1)
      narrow_two_buffers  1: the narrow shapes use the two-buffer layout of the wide-batch kernel too (default 0)
-     ks_group, pair_min_batch, tmk_stagger_ns, max_pbs_per_launch: see peba1_cuda.cu */
+     ks_group, ks_tile, ks_tile_parts, ks_tile_min: keyswitch forms that measured slower (several ciphertexts per CTA, register
+                      tiles); accepted by `make VARIANTS=all` builds only
+     pair_min_batch, tmk_stagger_ns, max_pbs_per_launch: see peba1_cuda.cu */
 int peba1_cuda_set_option(peba1_cuda_ctx* ctx, const char* name, int64_t value);
 
 #ifdef __cplusplus

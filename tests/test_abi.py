@@ -97,3 +97,14 @@ def test_plain_c_caller_fails_loudly_without_a_device():
                            "../../scripts/ubench/kbench_bin"])
     r = subprocess.run([os.path.join(ROOT, "scripts", "ubench", "kbench_bin"), "batch=8"], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr and r.stdout == ""
+
+
+def test_every_engine_option_is_documented_in_the_header():
+    """peba1_cuda_set_option's names (csrc/peba1_cuda.cu) all appear in include/peba1_cuda.h"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "peba1_b200", "csrc", "peba1_cuda.cu")).read()
+    hdr = open(os.path.join(root, "include", "peba1_cuda.h")).read()
+    names = re.findall(r'strcmp\(name, "([a-z_0-9]+)"\)', src[src.index("int peba1_cuda_set_option("):])
+    assert len(names) >= 10
+    assert [n for n in names if n not in hdr] == []
