@@ -50,7 +50,7 @@ def workload_config(args):
     return {"workload": f"gate-bootstrap microbench (BASELINE configs[1]): batch of {args.batch} boots{args.op} per GPU on "
                         "random ciphertexts, n=630 N=1024 k=1 l=3 Bgbit=7, keyswitch t=8 base 4",
             "batch_per_gpu": args.batch, "op": args.op,
-            "l2": "working set per step (inputs, extracted samples, outputs, keys) is 315 MB > 126 MB L2; no explicit flush"}
+            "l2": "working set per step (inputs, extracted samples, outputs, keys, the 1.34 GB keyswitch table) is 1.65 GB > 126 MB L2; no explicit flush"}
 
 
 def parse():
